@@ -1,0 +1,91 @@
+// Status strings, device properties, scratch allocation (host-side plumbing of libcommpy_b200.so).
+#include "common.cuh"
+
+namespace cpb {
+
+thread_local char g_cuda_err[256] = "";
+
+int record_cuda_error(cudaError_t e, const char *what, const char *file, int line)
+{
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s at %s:%d: %s", what, file, line, cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? CPB_ENOMEM : CPB_ECUDA;
+}
+
+const DeviceProps &device_props()
+{
+    static thread_local DeviceProps cache[64];
+    static thread_local bool have[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!have[dev]) {
+        DeviceProps p{};
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); p.sm_count = v;
+        cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev); p.cc_major = v;
+        cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev); p.cc_minor = v;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); p.smem_optin = (size_t)v;
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        p.global_mem = tot;
+        cache[dev] = p;
+        have[dev] = true;
+    }
+    return cache[dev];
+}
+
+int Scratch::acquire(void *user, size_t user_bytes, size_t need, cudaStream_t s)
+{
+    stream = s;
+    if (need == 0) { ptr = nullptr; owned = false; return CPB_OK; }
+    if (user != nullptr) {
+        if (user_bytes < need) return CPB_EINVAL;
+        ptr = user; owned = false;
+        return CPB_OK;
+    }
+    CPB_CUDA(cudaMallocAsync(&ptr, need, s));
+    owned = true;
+    return CPB_OK;
+}
+
+void Scratch::release()
+{
+    if (owned && ptr) cudaFreeAsync(ptr, stream);
+    ptr = nullptr; owned = false;
+}
+
+}  // namespace cpb
+
+extern "C" {
+
+const char *cpb_strerror(int status)
+{
+    switch (status) {
+    case CPB_OK: return "ok";
+    case CPB_EINVAL: return "invalid argument";
+    case CPB_EUNSUPPORTED: return "configuration not supported by the B200 path";
+    case CPB_ECUDA: return "CUDA runtime error (see cpb_last_cuda_error)";
+    case CPB_ENOMEM: return "out of device memory";
+    case CPB_ETRELLIS: return "trellis state without exactly 2^k predecessors";
+    default: return "unknown status";
+    }
+}
+
+const char *cpb_last_cuda_error(void) { return cpb::g_cuda_err; }
+
+int cpb_version(void) { return 100; }
+
+int cpb_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *global_mem_bytes)
+{
+    int n = 0;
+    CPB_CUDA(cudaGetDeviceCount(&n));
+    if (n <= 0) return CPB_ECUDA;
+    const cpb::DeviceProps &p = cpb::device_props();
+    if (sm_count) *sm_count = p.sm_count;
+    if (cc_major) *cc_major = p.cc_major;
+    if (cc_minor) *cc_minor = p.cc_minor;
+    if (global_mem_bytes) *global_mem_bytes = p.global_mem;
+    return CPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,48 @@
+"""Shared helpers for the parity tests: trellises, seeded channel inputs."""
+import warnings
+
+import numpy as np
+
+from commpy_b200.channelcoding.convcode import Trellis, conv_encode
+
+
+def k7():
+    return Trellis(np.array([6]), np.array([[0o133, 0o171]]))
+
+
+def k7_wifi_quirk():
+    """Trellis of DECIMAL (133, 171) as commpy/wifi80211.py:49 builds it (taps 5, 43)."""
+    return Trellis(np.array([6]), np.array([[133, 171]]))
+
+
+def reference_test_trellises():
+    """The five trellises of commpy/channelcoding/tests/test_convcode.py:23-111."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return [
+            Trellis(np.array([2]), np.array([[5, 7]]), code_type="default"),
+            Trellis(np.array([2]), np.array([[1, 7]]), 5, "rsc"),
+            Trellis(np.array([2, 1]), np.array([[5, 7, 0], [0, 2, 3]]), code_type="default"),
+            Trellis(np.array([2, 1]), np.array([[5, 7, 0], [0, 2, 6]]), code_type="default", polynomial_format="LSB"),
+            Trellis(np.array([1, 1]), np.array([[1, 0, 0], [0, 1, 3]]), np.array([[2, 2], [3, 1]]), "rsc"),
+        ]
+
+
+def rsc_k4():
+    """K=4 RSC (8 states) of SURVEY.md section 8c: Trellis([3], [[1, 0o15]], [[0o13]], 'rsc')."""
+    return Trellis(np.array([3]), np.array([[1, 0o15]]), np.array([[0o13]]), "rsc")
+
+
+def channel_frames(trellis, rs, batch, nbits, mode, termination="cont", flip=0.03, ebn0_db=4.0):
+    """Encode `batch` random messages and pass them through BSC (hard) or BPSK-AWGN (soft: LLR = 2y/sigma^2,
+    positive favours 1; unquantized: y).  Returns (msgs, channel_values)."""
+    msgs = rs.randint(0, 2, (batch, nbits))
+    coded = np.stack([conv_encode(m, trellis, termination) for m in msgs]).astype(np.float64)
+    rate = trellis.k / trellis.n
+    if mode == "hard":
+        x = np.abs(coded - (rs.rand(*coded.shape) < flip))
+    else:
+        sigma2 = 1.0 / (2.0 * rate * 10 ** (ebn0_db / 10.0))
+        y = (2 * coded - 1) + np.sqrt(sigma2) * rs.randn(*coded.shape)
+        x = 2 * y / sigma2 if mode == "soft" else y
+    return msgs, x

@@ -1,0 +1,92 @@
+"""GPU parity: cpb_viterbi_decode (through the CommPy-shaped Python wrappers) against the CPU oracle."""
+import numpy as np
+import pytest
+
+import helpers
+from oracle import oracle
+from commpy_b200.channelcoding import viterbi_decode, viterbi_decode_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _agree(got, want):
+    return float((np.asarray(got) == np.asarray(want)).mean())
+
+
+@pytest.mark.parametrize("make", [helpers.k7, helpers.k7_wifi_quirk])
+@pytest.mark.parametrize("tb", [None, 15, 7, 48])
+@pytest.mark.parametrize("term", ["cont", "term"])
+def test_k7_hard_bit_exact(make, tb, term):
+    tr = make()
+    rs = np.random.RandomState(11)
+    for nbits, flip in ((200, 0.12), (1024, 0.03), (333, 0.06)):
+        _, x = helpers.channel_frames(tr, rs, 70, nbits, "hard", term, flip=flip)
+        want = oracle.viterbi_decode_batch(x, tr, tb, "hard")
+        got = viterbi_decode_batch(x.astype(np.uint8), tr, tb, "hard")
+        assert got.dtype == np.uint8 and got.shape == want.shape
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("mode", ["soft", "unquantized"])
+@pytest.mark.parametrize("tb", [None, 15])
+def test_k7_float_agreement(mode, tb):
+    tr = helpers.k7()
+    rs = np.random.RandomState(12)
+    tot = 0
+    bad = 0
+    for nbits, eb in ((256, 0.0), (1024, 2.0), (1024, 4.0)):
+        msgs, x = helpers.channel_frames(tr, rs, 64, nbits, mode, "cont", ebn0_db=eb)
+        want = oracle.viterbi_decode_batch(x, tr, tb, mode)
+        got = viterbi_decode_batch(x.astype(np.float32), tr, tb, mode)
+        tot += want.size
+        bad += int((got != want).sum())
+        # BER against the transmitted message must match the oracle's within a few bits
+        assert abs(int((got != msgs).sum()) - int((want != msgs).sum())) <= max(8, 0.02 * (want != msgs).sum())
+    assert bad / tot <= 1e-4, "bit agreement %.6f" % (1 - bad / tot)
+
+
+def test_generic_trellises_all_modes():
+    rs = np.random.RandomState(13)
+    for tr in helpers.reference_test_trellises() + [helpers.rsc_k4()]:
+        for mode in ("hard", "soft", "unquantized"):
+            for term in ("cont", "term"):
+                nb = 120 * tr.k
+                _, x = helpers.channel_frames(tr, rs, 33, nb, mode, term, flip=0.08, ebn0_db=1.0)
+                for tb in (None, 15, 5):
+                    want = oracle.viterbi_decode_batch(x, tr, tb, mode)
+                    xin = x.astype(np.uint8) if mode == "hard" else x.astype(np.float32)
+                    got = viterbi_decode_batch(xin, tr, tb, mode)
+                    if mode == "hard":
+                        assert np.array_equal(got, want), (tr.k, tr.n, mode, term, tb)
+                    else:
+                        assert _agree(got, want) >= 0.999, (tr.k, tr.n, mode, term, tb, _agree(got, want))
+
+
+def test_single_frame_signature_and_errors():
+    tr = helpers.k7()
+    rs = np.random.RandomState(14)
+    msgs, x = helpers.channel_frames(tr, rs, 1, 300, "hard", "term", flip=0.02)
+    out = viterbi_decode(x[0], tr)
+    assert out.ndim == 1 and out.dtype == np.dtype("int") and len(out) == 306
+    assert np.array_equal(out, oracle.viterbi_decode(x[0], tr))
+    with pytest.raises(ValueError):
+        viterbi_decode(x[0], tr, decoding_type="bogus")
+    with pytest.raises(ValueError):
+        viterbi_decode(x[0] * 3, tr)
+    with pytest.raises(ValueError):
+        viterbi_decode(x[0][:20], tr, tb_depth=40)
+
+
+def test_reference_roundtrips_inf_llr():
+    """commpy/channelcoding/tests/test_convcode.py:133-178: noiseless / +-inf LLR round trips, tb_depth 15."""
+    from commpy_b200.channelcoding import conv_encode
+    rs = np.random.RandomState(17121996 % (2 ** 31))
+    for tr in helpers.reference_test_trellises() + [helpers.k7()]:
+        msg = rs.randint(0, 2, 1000 - 1000 % tr.k)
+        coded = conv_encode(msg, tr)
+        assert np.array_equal(viterbi_decode(coded.astype(float), tr, 15)[:len(msg)], msg)
+        assert np.array_equal(viterbi_decode(2.0 * coded - 1, tr, 15, "unquantized")[:len(msg)], msg)
+        assert np.array_equal(viterbi_decode((2.0 * coded - 1) * np.inf, tr, 15, "soft")[:len(msg)], msg)
+        cont = conv_encode(msg, tr, termination="cont")
+        noisy = 10.0 * cont - 5 + rs.randn(len(cont)) * 2
+        assert np.array_equal(viterbi_decode(noisy, tr, 15, "soft"), msg)
