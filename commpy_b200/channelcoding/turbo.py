@@ -1,0 +1,102 @@
+"""Turbo codes: encoder (host) and BCJR / turbo decoding on the GPU.
+
+Mirror of commpy/channelcoding/turbo.py.  `map_decode` / `turbo_decode` run in CUDA
+(commpy_b200/csrc/bcjr.cu) through `cpb_map_decode` / `cpb_turbo_decode`; there is no CPU decode path.
+The kernels use the log-domain exact max* instead of the reference's renormalised probabilities -- the
+same algorithm (log-MAP), float32 instead of float64: LLRs agree to ~1e-5 where the reference is finite
+(it returns +-inf once its exponentials underflow; the GPU path stays finite there).
+"""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+from .convcode import _trellis_handle, conv_encode
+
+__all__ = ["turbo_encode", "map_decode", "turbo_decode", "map_decode_batch", "turbo_decode_batch"]
+
+
+def turbo_encode(msg_bits, trellis1, trellis2, interleaver):
+    """Rate-1/3 parallel concatenation (turbo.py:14-59): returns [sys, parity1, parity2].
+
+    Exactly like the reference the two RSC encoders run 'rsc'-terminated and the last `total_memory`
+    entries of each stream are dropped; the second parity stream comes from a punctured conv_encode whose
+    output keeps its unpunctured length, so it is longer than the other two."""
+    stream = conv_encode(msg_bits, trellis1, "rsc")
+    sys_stream = stream[::2]
+    non_sys_stream_1 = stream[1::2]
+    interlv_msg_bits = interleaver.interlv(sys_stream)
+    non_sys_stream_2 = conv_encode(interlv_msg_bits, trellis2, "rsc", np.array([[0, 1]]))
+    m1, m2 = trellis1.total_memory, trellis2.total_memory
+    return [sys_stream[0:-m1], non_sys_stream_1[0:-m1], non_sys_stream_2[0:-m2]]
+
+
+def _dev_f32(x, torch):
+    if hasattr(x, "data_ptr"):
+        t = x if x.is_cuda else x.cuda()
+        return t.to(torch.float32).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).cuda()
+
+
+def map_decode_batch(sys_symbols, non_sys_symbols, trellis, noise_variance, L_int, mode="decode"):
+    """Batched MAP decoder: (batch, N) inputs -> (L (batch, N) float32, bits (batch, N) uint8) torch CUDA tensors."""
+    torch = _lib.require_cuda()
+    s = _dev_f32(sys_symbols, torch)
+    p = _dev_f32(non_sys_symbols, torch)
+    la = _dev_f32(L_int, torch)
+    if s.dim() != 2 or s.shape != p.shape or s.shape != la.shape:
+        raise ValueError("sys_symbols, non_sys_symbols and L_int must share the shape (batch, N)")
+    batch, N = s.shape
+    L = torch.empty_like(s)
+    bits = torch.empty((batch, N), dtype=torch.uint8, device=s.device)
+    rc = _lib.load().cpb_map_decode(_trellis_handle(trellis), _lib.ptr(s), _lib.ptr(p), _lib.ptr(la),
+                                    C.c_int64(batch), C.c_int64(N), C.c_float(noise_variance),
+                                    1 if mode == "decode" else 0, _lib.ptr(L), _lib.ptr(bits), _lib.stream_ptr(torch))
+    _lib.check(rc, "map_decode")
+    return L, bits
+
+
+def map_decode(sys_symbols, non_sys_symbols, trellis, noise_variance, L_int, mode="decode"):
+    """Drop-in for commpy.channelcoding.map_decode (turbo.py:163-251): returns [L_ext, decoded_bits].
+
+    `L_ext` is, as in the reference, the full a-posteriori LLR  L_int + log(app1/app0)  (:145-146);
+    `decoded_bits` is (L_ext > 0) in mode 'decode' and zeros in mode 'compute' (:148-152)."""
+    L, bits = map_decode_batch(np.asarray(sys_symbols)[None, :], np.asarray(non_sys_symbols)[None, :], trellis,
+                               noise_variance, np.asarray(L_int)[None, :], mode)
+    return [L[0].cpu().numpy().astype(np.float64), bits[0].cpu().numpy().astype("int")]
+
+
+def turbo_decode_batch(sys_symbols, non_sys_symbols_1, non_sys_symbols_2, trellis, noise_variance,
+                       number_iterations, interleaver, L_int=None):
+    """Batched turbo decoder: (batch, N) inputs -> (batch, N) uint8 torch CUDA tensor."""
+    torch = _lib.require_cuda()
+    s = _dev_f32(sys_symbols, torch)
+    p1 = _dev_f32(non_sys_symbols_1, torch)
+    p2 = _dev_f32(non_sys_symbols_2, torch)
+    if s.dim() != 2 or s.shape != p1.shape or s.shape != p2.shape:
+        raise ValueError("the three symbol streams must share the shape (batch, N)")
+    batch, N = s.shape
+    perm_np = np.ascontiguousarray(interleaver.p_array, dtype=np.int32)
+    if len(perm_np) != N:
+        raise ValueError("interleaver length does not match the frame length")
+    perm = torch.from_numpy(perm_np).cuda()
+    la = None if L_int is None else _dev_f32(L_int, torch)
+    bits = torch.empty((batch, N), dtype=torch.uint8, device=s.device)
+    rc = _lib.load().cpb_turbo_decode(_trellis_handle(trellis), _lib.ptr(s), _lib.ptr(p1), _lib.ptr(p2), _lib.ptr(perm),
+                                      C.c_int64(batch), C.c_int64(N), C.c_float(noise_variance),
+                                      int(number_iterations), _lib.ptr(la), _lib.ptr(bits), _lib.stream_ptr(torch))
+    _lib.check(rc, "turbo_decode")
+    return bits
+
+
+def turbo_decode(sys_symbols, non_sys_symbols_1, non_sys_symbols_2, trellis, noise_variance,
+                 number_iterations, interleaver, L_int=None):
+    """Drop-in for commpy.channelcoding.turbo_decode (turbo.py:254-333): 1-D in, 1-D int out.
+
+    Keeps the reference's loop exactly, including the systematic double counting (only the prior is removed
+    from each decoder's output, :318 and :328) and the final de-interleave of decoder 2's hard decisions (:331)."""
+    la = None if L_int is None else np.asarray(L_int)[None, :]
+    bits = turbo_decode_batch(np.asarray(sys_symbols)[None, :], np.asarray(non_sys_symbols_1)[None, :],
+                              np.asarray(non_sys_symbols_2)[None, :], trellis, noise_variance, number_iterations,
+                              interleaver, la)
+    return bits[0].cpu().numpy().astype("int")

@@ -609,6 +609,7 @@ int cpb_trellis_fast_path(const cpbTrellis *t) { return t ? t->fast_id : 0; }
 // tables for the BCJR kernels (bcjr.cu)
 const int32_t *cpb_trellis_next_dev(const cpbTrellis *t) { return t->next_dev; }
 const int32_t *cpb_trellis_out_dev(const cpbTrellis *t) { return t->out_dev; }
+const int32_t *cpb_trellis_pred_dev(const cpbTrellis *t) { return t->pred_dev; }
 void cpb_trellis_dims(const cpbTrellis *t, int *k, int *n, int *S) { *k = t->k; *n = t->n; *S = t->S; }
 
 static int resolve_depth(const cpbTrellis *t, int64_t L, int tb_depth)

@@ -1,0 +1,229 @@
+"""GPU parity for BCJR/turbo, LDPC min-sum, the demapper and the error counter: CUDA kernels (through the
+CommPy-shaped wrappers) against the golden vectors of the reference and against the CPU oracle."""
+import os
+from itertools import product
+
+import numpy as np
+import pytest
+
+import helpers
+from oracle import oracle
+from commpy_b200.channelcoding import (RandInterlv, conv_encode, ldpc_bp_decode, ldpc_bp_decode_batch, map_decode,
+                                        map_decode_batch, turbo_decode, turbo_decode_batch, turbo_encode)
+from commpy_b200.modulation import Modem, PSKModem, QAMModem
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# stated tolerances
+MAP_ATOL, MAP_RTOL = 1e-4, 1e-4
+DEMAP_ATOL, DEMAP_RTOL = 5e-4, 5e-4
+
+
+def _spec_trellis(name):
+    from test_host_mirror import _specs
+    import warnings
+    from commpy_b200.channelcoding import Trellis
+    mem, g, fb, ct, pf = _specs()[name]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return Trellis(mem, g, fb, ct, pf)
+
+
+# ---------------------------------------------------------------- BCJR / turbo
+def test_map_decode_golden_llr_tolerance():
+    g = np.load(os.path.join(GOLD, "bcjr_turbo.npz"))
+    worst = 0.0
+    for c in range(9):
+        name, s2 = g["m%02d_meta" % c]
+        tr = _spec_trellis(str(name))
+        L, bits = map_decode(g["m%02d_sys" % c], g["m%02d_par" % c], tr, float(s2), g["m%02d_La" % c], "decode")
+        ref = g["m%02d_L" % c]
+        fin = np.isfinite(ref)
+        err = np.abs(L[fin] - ref[fin]) - MAP_RTOL * np.abs(ref[fin])
+        worst = max(worst, float(err.max()))
+        assert (err <= MAP_ATOL).all(), (name, float(err.max()))
+        safe = np.abs(ref) > 1e-3
+        assert np.array_equal(bits[safe], g["m%02d_bits" % c][safe])
+        L2, b2 = map_decode(g["m%02d_sys" % c], g["m%02d_par" % c], tr, float(s2), g["m%02d_La" % c], "compute")
+        assert np.allclose(L2, L) and not b2.any() and b2.dtype == np.dtype("int")
+    print("map_decode worst excess error", worst)
+
+
+def test_map_decode_batch_vs_oracle_long_frames():
+    tr = helpers.rsc_k4()
+    rs = np.random.RandomState(21)
+    N, batch = 6144, 6
+    msgs = rs.randint(0, 2, (batch, N))
+    coded = np.stack([conv_encode(m, tr, "cont") for m in msgs])
+    s2 = 1.0 / (2 * 0.5 * 10 ** (1.0 / 10))
+    ys = 2.0 * coded[:, 0::2] - 1 + np.sqrt(s2) * rs.randn(batch, N)
+    yp = 2.0 * coded[:, 1::2] - 1 + np.sqrt(s2) * rs.randn(batch, N)
+    La = rs.randn(batch, N)
+    L, bits = map_decode_batch(ys, yp, tr, s2, La, "decode")
+    L = L.cpu().numpy()
+    for b in range(batch):
+        Lo, bo = oracle.map_decode(ys[b], yp[b], tr, s2, La[b], "decode")
+        assert (np.abs(L[b] - Lo) <= MAP_ATOL + MAP_RTOL * np.abs(Lo)).all(), float(np.abs(L[b] - Lo).max())
+
+
+def test_turbo_decode_golden_and_batch():
+    g = np.load(os.path.join(GOLD, "bcjr_turbo.npz"))
+    tr = helpers.rsc_k4()
+
+    class IL:
+        pass
+    tot = bad = 0
+    for c in range(3):
+        s2, iters = g["t%02d_meta" % c]
+        il = IL()
+        il.p_array = g["t%02d_perm" % c]
+        bits = turbo_decode(g["t%02d_sys" % c], g["t%02d_p1" % c], g["t%02d_p2" % c], tr, float(s2), int(iters), il)
+        assert bits.dtype == np.dtype("int")
+        tot += bits.size
+        bad += int((bits != g["t%02d_bits" % c]).sum())
+    assert bad / tot <= 1e-3, (bad, tot)
+    # batch at the C3 frame length: agreement with the oracle and with the message
+    rs = np.random.RandomState(22)
+    N, batch = 6144, 8
+    il = RandInterlv(N, 1)
+    s2 = 1.0 / (2 * (1 / 3) * 10 ** (1.0 / 10))
+    ys, y1, y2, msgs = [], [], [], []
+    for b in range(batch):
+        msg = rs.randint(0, 2, N)
+        s_, p1, p2 = turbo_encode(msg, tr, tr, il)
+        ys.append(2.0 * s_[:N] - 1 + np.sqrt(s2) * rs.randn(N))
+        y1.append(2.0 * p1[:N] - 1 + np.sqrt(s2) * rs.randn(N))
+        y2.append(2.0 * p2[:N] - 1 + np.sqrt(s2) * rs.randn(N))
+        msgs.append(msg)
+    ys, y1, y2, msgs = map(np.stack, (ys, y1, y2, msgs))
+    got = turbo_decode_batch(ys, y1, y2, tr, s2, 6, il).cpu().numpy()
+    want = oracle.turbo_decode_batch(ys, y1, y2, tr, s2, 6, il, threads=8)
+    assert (got == want).mean() >= 0.999, float((got == want).mean())
+    assert abs(int((got != msgs).sum()) - int((want != msgs).sum())) <= max(10, 0.05 * (want != msgs).sum())
+
+
+# ---------------------------------------------------------------- LDPC
+def _golden_ldpc(c):
+    import scipy.sparse as sp
+    g = np.load(os.path.join(GOLD, "ldpc.npz"))
+    rel, nblk, iters, m, n = g["l%02d_meta" % c]
+    H = sp.csr_matrix((np.ones(len(g["l%02d_indices" % c]), np.int8), g["l%02d_indices" % c], g["l%02d_indptr" % c]),
+                      shape=(int(m), int(n)))
+    return g, {"n_vnodes": int(n), "n_cnodes": int(m), "parity_check_matrix": H.tocsc()}, int(iters)
+
+
+def test_ldpc_fp64_bit_exact_with_reference():
+    for c in range(5):
+        g, params, iters = _golden_ldpc(c)
+        llr = g["l%02d_llr" % c].copy()
+        dec, out = ldpc_bp_decode(llr, params, "MSA", iters)          # default precision: fp64 parity mode
+        assert dec.dtype == np.int8
+        assert np.array_equal(dec, g["l%02d_dec" % c]), c
+        assert np.array_equal(out, g["l%02d_out" % c]), (c, float(np.abs(out - g["l%02d_out" % c]).max()))
+        assert np.abs(llr).max() <= 500.0                               # clipped in place (ldpc.py:186)
+    with pytest.raises(NameError):
+        ldpc_bp_decode(np.zeros(params["n_vnodes"]), params, "XYZ", 3)
+
+
+def test_ldpc_fp32_converged_frames_match():
+    g, params, _ = _golden_ldpc(3)                    # WiMax 1440.720
+    n = params["n_vnodes"]
+    rs = np.random.RandomState(23)
+    sigma = 1.0 / np.sqrt(2 * 0.5 * 10 ** (2.5 / 10))
+    batch = 48
+    llr = (2.0 * (1.0 + sigma * rs.randn(batch, n)) / sigma ** 2)
+    want_dec, want_out, want_it = oracle.ldpc_bp_decode(llr.reshape(-1).copy(), params, "MSA", 50, return_iters=True,
+                                                        threads=8)
+    dec, out, it = ldpc_bp_decode_batch(llr.astype(np.float32), params, 50, "fp32", return_iters=True)
+    dec, out, it = dec.cpu().numpy(), out.cpu().numpy(), it.cpu().numpy()
+    conv = want_it < 50
+    assert conv.sum() >= batch // 2
+    want_dec = want_dec.reshape(n, batch).T if batch > 1 else want_dec[None]
+    want_out = want_out.reshape(n, batch).T if batch > 1 else want_out[None]
+    assert np.array_equal(dec[conv], want_dec[conv])
+    assert np.array_equal(it[conv], want_it[conv])
+    assert np.allclose(out[conv], want_out[conv], rtol=1e-4, atol=1e-3)
+    # fp64 mode: every frame, converged or not, exact
+    dec64, out64, it64 = ldpc_bp_decode_batch(llr, params, 50, "fp64", return_iters=True)
+    assert np.array_equal(dec64.cpu().numpy(), want_dec)
+    assert np.array_equal(out64.cpu().numpy(), want_out)
+    assert np.array_equal(it64.cpu().numpy(), want_it)
+
+
+def test_ldpc_noiseless_roundtrip_and_zero_iterations():
+    """test_ldpc.py:77-106: a noiseless codeword needs zero iterations and out_llrs stays the clipped input."""
+    g, params, _ = _golden_ldpc(3)
+    n = params["n_vnodes"]
+    llr = np.full(n, 1000.0)
+    dec, out = ldpc_bp_decode(llr, params, "MSA", 10)
+    assert not dec.any() and np.array_equal(out, np.full(n, 500.0)) and llr.max() == 500.0
+
+
+# ---------------------------------------------------------------- demapper
+def test_demod_soft_golden_tolerance_and_hard_exact():
+    g = np.load(os.path.join(GOLD, "demod.npz"))
+    custom = [re + im * 1j for re, im in product((-3.5, -0.5, 0.5, 3.5), repeat=2)]
+    mods = {"psk4": PSKModem(4), "psk8": PSKModem(8), "psk16": PSKModem(16), "qam4": QAMModem(4),
+            "qam16": QAMModem(16), "qam64": QAMModem(64), "qam256": QAMModem(256), "custom16": Modem(custom)}
+    worst = 0.0
+    for c in range(24):
+        name, nv = g["d%02d_meta" % c]
+        md = mods[str(name)]
+        y = g["d%02d_y" % c]
+        ref = g["d%02d_llr" % c]
+        out = md.demodulate(y, "soft", float(nv))
+        assert out.dtype == np.float64 and out.shape == ref.shape
+        fin = np.isfinite(ref)
+        err = np.abs(out[fin] - ref[fin]) - DEMAP_RTOL * np.abs(ref[fin])
+        worst = max(worst, float(err.max()))
+        assert (err <= DEMAP_ATOL).all(), (name, nv, float(err.max()))
+        assert np.isfinite(out).all()
+        hard = md.demodulate(y, "hard")
+        assert hard.dtype == np.int8 and np.array_equal(hard, g["d%02d_hard" % c]), name
+    print("demod worst excess error", worst)
+    with pytest.raises(ValueError):
+        mods["qam16"].demodulate(np.zeros(4, complex), "medium")
+
+
+def test_demod_roundtrip_all_patterns():
+    """test_modulation.py:159-162: modulate -> hard demodulate is the identity for every bit pattern."""
+    for md in (QAMModem(4), QAMModem(16), QAMModem(64), PSKModem(4), PSKModem(16), PSKModem(64)):
+        for bits in product(*((0, 1),) * md.num_bits_symbol):
+            assert np.array_equal(bits, md.demodulate(md.modulate(bits), "hard"))
+
+
+def test_demod_separable_equals_general_path():
+    import torch
+    q = QAMModem(256)
+    gen = Modem(q.constellation, reorder_as_gray=False)
+    gen._constellation = gen._constellation * (1 + 0j)
+    rs = np.random.RandomState(24)
+    y = (rs.randn(4096) + 1j * rs.randn(4096)) * 9
+    a = q.demodulate(y, "soft", 12.0)
+    # force the general kernel by perturbing one point by one ulp-ish amount
+    pts = np.array(q.constellation, dtype=np.complex128)
+    pts[3] += 1e-6
+    gen.constellation = pts
+    b = gen.demodulate(y, "soft", 12.0)
+    assert np.allclose(a, b, rtol=2e-3, atol=2e-3)
+
+
+# ---------------------------------------------------------------- error counter
+def test_count_errors():
+    import ctypes as C
+    import torch
+    from commpy_b200 import _lib
+    rs = np.random.RandomState(25)
+    a = rs.randint(0, 2, (513, 1030)).astype(np.uint8)
+    b = a.copy()
+    flips = rs.rand(*a.shape) < 0.01
+    flips[::7] = False
+    b[flips] ^= 1
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+    rc = _lib.load().cpb_count_errors(_lib.ptr(ta), _lib.ptr(tb), C.c_int64(513), C.c_int64(1030), C.c_int64(1030),
+                                      C.c_int64(1030), _lib.ptr(cnt), _lib.stream_ptr(torch))
+    _lib.check(rc, "count")
+    got = cnt.cpu().numpy()
+    assert got[0] == int(flips.sum()) and got[1] == int(flips.any(axis=1).sum())
