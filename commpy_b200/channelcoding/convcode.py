@@ -247,59 +247,69 @@ def _check_depth(trellis, L, T, tb_depth):
     return D
 
 
+def _host_buffer(coded, hard, torch):
+    """numpy array / CPU torch tensor -> (object keeping it alive, pointer source, batch, n_in) in the kernel's dtype."""
+    if hasattr(coded, "data_ptr"):
+        want = torch.uint8 if hard else torch.float32
+        x = coded if coded.dtype == want else coded.to(want)
+        x = x.contiguous()
+        return x, x.shape[0], x.shape[1]
+    a = np.asarray(coded)
+    if hard:
+        ai = a if a.dtype == np.uint8 else a.astype(np.int64)          # astype(int): convcode.py:579
+        if ai.size and (ai.min() < 0 or ai.max() > 1):
+            raise ValueError("hard-decision input must contain only 0 and 1")
+        a = np.ascontiguousarray(ai, dtype=np.uint8)
+    else:
+        a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.shape[0], a.shape[1]
+
+
 def viterbi_decode_batch(coded, trellis, tb_depth=None, decoding_type="hard", out=None):
     """Decode a batch of independent frames on the GPU.
 
-    coded : (batch, n_in) array.  numpy (host) or torch CUDA tensor.  'hard': integer / bool / float values
-            in {0, 1} (uint8 is the zero-copy layout); 'soft' / 'unquantized': float32 is zero-copy.
-    Returns (batch, L) uint8 bits, as a torch CUDA tensor when `coded` was one, else a numpy array.
+    coded : (batch, n_in) array.  'hard': values in {0, 1} (uint8 is the zero-copy layout);
+            'soft' / 'unquantized': float32 is zero-copy.
+        * torch CUDA tensor -> decoded in place on the current stream, returns a (batch, L) uint8 CUDA tensor;
+        * numpy array or CPU torch tensor (pinned memory overlaps best) -> `cpb_viterbi_decode_host`: chunked
+          H2D / decode / D2H pipeline, returns a numpy array (or CPU tensor) of uint8 bits.
+    `out` may supply the result buffer (same kind as the input).
     """
     if decoding_type not in _lib.VITERBI_MODES:
         raise ValueError(_MODE_ERR)
     torch = _lib.require_cuda()
     lib = _lib.load()
-    is_torch = hasattr(coded, "data_ptr")
     hard = decoding_type == "hard"
-    if is_torch:
+    if getattr(coded, "ndim", None) != 2 and not (hasattr(coded, "dim") and coded.dim() == 2):
+        raise ValueError("coded must be (batch, n_in)")
+    on_device = hasattr(coded, "data_ptr") and coded.is_cuda
+    handle = _trellis_handle(trellis)
+    if on_device:
         x = coded
-        if x.dim() != 2:
-            raise ValueError("coded must be (batch, n_in)")
-        if not x.is_cuda:
-            x = x.cuda(non_blocking=True)
-        if hard:
-            if x.dtype != torch.uint8:
-                x = x.to(torch.uint8)
-        elif x.dtype != torch.float32:
-            x = x.to(torch.float32)
+        want = torch.uint8 if hard else torch.float32
+        if x.dtype != want:
+            x = x.to(want)
         x = x.contiguous()
-    else:
-        a = np.asarray(coded)
-        if a.ndim != 2:
-            raise ValueError("coded must be (batch, n_in)")
-        if hard:
-            ai = a if a.dtype == np.uint8 else a.astype(np.int64)      # astype(int): convcode.py:579
-            if ai.size and (ai.min() < 0 or ai.max() > 1):
-                raise ValueError("hard-decision input must contain only 0 and 1")
-            a = np.ascontiguousarray(ai, dtype=np.uint8)
-        else:
-            a = np.ascontiguousarray(a, dtype=np.float32)
-        x = torch.from_numpy(a).cuda()
-    batch, n_in = x.shape
+        batch, n_in = x.shape
+        L, T = _sizes(trellis, n_in)
+        _check_depth(trellis, L, T, tb_depth)
+        out_t = torch.empty((batch, L), dtype=torch.uint8, device=x.device) if out is None else out
+        rc = lib.cpb_viterbi_decode(handle, _lib.ptr(x), _lib.CPB_U8 if hard else _lib.CPB_F32,
+                                    C.c_int64(batch), C.c_int64(n_in), int(tb_depth or 0),
+                                    _lib.VITERBI_MODES[decoding_type], _lib.ptr(out_t),
+                                    C.c_void_p(0), C.c_size_t(0), _lib.stream_ptr(torch))
+        _lib.check(rc, "viterbi_decode")
+        return out_t
+    x, batch, n_in = _host_buffer(coded, hard, torch)
     L, T = _sizes(trellis, n_in)
     _check_depth(trellis, L, T, tb_depth)
     if out is None:
-        out_t = torch.empty((batch, L), dtype=torch.uint8, device=x.device)
-    else:
-        out_t = out
-    handle = _trellis_handle(trellis)
-    rc = lib.cpb_viterbi_decode(handle, _lib.ptr(x), _lib.CPB_U8 if hard else _lib.CPB_F32,
-                                C.c_int64(batch), C.c_int64(n_in), int(tb_depth or 0),
-                                _lib.VITERBI_MODES[decoding_type], _lib.ptr(out_t),
-                                C.c_void_p(0), C.c_size_t(0), _lib.stream_ptr(torch))
+        out = torch.empty((batch, L), dtype=torch.uint8) if hasattr(coded, "data_ptr") else np.empty((batch, L), np.uint8)
+    rc = lib.cpb_viterbi_decode_host(handle, _lib.ptr(x), _lib.CPB_U8 if hard else _lib.CPB_F32, C.c_int64(batch),
+                                     C.c_int64(n_in), int(tb_depth or 0), _lib.VITERBI_MODES[decoding_type],
+                                     _lib.ptr(out))
     _lib.check(rc, "viterbi_decode")
-    if is_torch:
-        return out_t
-    return out_t.cpu().numpy()
+    return out
 
 
 def viterbi_decode(coded_bits, trellis, tb_depth=None, decoding_type="hard"):

@@ -30,7 +30,6 @@ struct cpbModem {
 
 namespace demap {
 
-constexpr int MAXNB = 12;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
@@ -38,6 +37,11 @@ struct SepTables {
     float pi[64];
     float pq[64];
 };
+
+// log2 of a group sum is off + log2(sum).  Sums are accumulated relative to the GLOBAL nearest point (off = -dmin);
+// when a whole group lies more than ~100 octaves further away its fp32 sum underflows, and only then it is
+// re-accumulated relative to the group's own nearest point (rare: |LLR| > 69).
+constexpr float TINY = 7.8886e-31f;     // 2^-100
 
 // one axis of a separable constellation: R levels, HB = log2(R) bits; out[h] = LLR of axis bit h (LSB = 0)
 template <int HB>
@@ -64,7 +68,25 @@ __device__ __forceinline__ void axis_llr(float y, const float *__restrict__ lev,
         }
     }
 #pragma unroll
-    for (int h = 0; h < HB; ++h) out[h] = (__log2f(num[h]) - __log2f(den[h])) * LN2;
+    for (int h = 0; h < HB; ++h) {
+        float l1 = __log2f(num[h]), l0 = __log2f(den[h]);
+        if (fminf(num[h], den[h]) < TINY) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                if ((g ? num[h] : den[h]) >= TINY) continue;
+                float dg = 3.0e38f, sg = 0.0f;
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+                    if (((i >> h) & 1) == g) dg = fminf(dg, d[i]);
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+                    if (((i >> h) & 1) == g) sg += exp2f(dg - d[i]);
+                const float l = (dmin - dg) + __log2f(sg);
+                if (g) l1 = l; else l0 = l;
+            }
+        }
+        out[h] = (l1 - l0) * LN2;
+    }
 }
 
 template <int HB>
@@ -128,7 +150,28 @@ __global__ void __launch_bounds__(256) demod_soft_general(const float2 *__restri
     }
     float *dst = llr + i * NB;
 #pragma unroll
-    for (int b = 0; b < NB; ++b) dst[NB - 1 - b] = (__log2f(num[b]) - __log2f(den[b])) * LN2;
+    for (int b = 0; b < NB; ++b) {
+        float l1 = __log2f(num[b]), l0 = __log2f(den[b]);
+        if (fminf(num[b], den[b]) < TINY) {          // a whole group underflowed: redo it against its own nearest point
+            for (int g = 0; g < 2; ++g) {
+                if ((g ? num[b] : den[b]) >= TINY) continue;
+                float dg = 3.0e38f, sg = 0.0f;
+                for (int k = 0; k < M; ++k)
+                    if (((k >> b) & 1) == g) {
+                        const float a = v.x - sc[k].x, b2 = v.y - sc[k].y;
+                        dg = fminf(dg, (a * a + b2 * b2) * inv_nv_log2e);
+                    }
+                for (int k = 0; k < M; ++k)
+                    if (((k >> b) & 1) == g) {
+                        const float a = v.x - sc[k].x, b2 = v.y - sc[k].y;
+                        sg += exp2f(dg - (a * a + b2 * b2) * inv_nv_log2e);
+                    }
+                const float l = (dmin - dg) + __log2f(sg);
+                if (g) l1 = l; else l0 = l;
+            }
+        }
+        dst[NB - 1 - b] = (l1 - l0) * LN2;
+    }
 }
 
 __global__ void __launch_bounds__(256) demod_hard_kernel(const float2 *__restrict__ y, int64_t nsym,

@@ -33,11 +33,36 @@ def rsc_k4():
     return Trellis(np.array([3]), np.array([[1, 0o15]]), np.array([[0o13]]), "rsc")
 
 
+def encode_batch(msgs, trellis, termination="cont"):
+    """conv_encode for a (batch, nbits) array of messages: the table walk of convcode.py:535-540 vectorised over
+    frames (checked against conv_encode in tests/test_host_mirror.py)."""
+    msgs = np.asarray(msgs)
+    k, n, M = trellis.k, trellis.n, trellis.total_memory
+    if termination == "term":
+        if trellis.code_type == "rsc":
+            return np.stack([conv_encode(m, trellis, termination) for m in msgs])
+        msgs = np.concatenate([msgs, np.zeros((msgs.shape[0], M + M % k), msgs.dtype)], axis=1)
+    batch, nin = msgs.shape
+    steps = nin // k
+    nst = np.asarray(trellis.next_state_table)
+    otab = np.asarray(trellis.output_table)
+    words = msgs[:, :steps * k].reshape(batch, steps, k) @ (1 << np.arange(k - 1, -1, -1))
+    state = np.zeros(batch, dtype=np.int64)
+    out = np.zeros((batch, int(nin / (k / n))), dtype=np.int64)
+    shifts = np.arange(n - 1, -1, -1)
+    for t in range(steps):
+        w = words[:, t]
+        o = otab[state, w]
+        out[:, t * n:(t + 1) * n] = (o[:, None] >> shifts) & 1
+        state = nst[state, w]
+    return out
+
+
 def channel_frames(trellis, rs, batch, nbits, mode, termination="cont", flip=0.03, ebn0_db=4.0):
     """Encode `batch` random messages and pass them through BSC (hard) or BPSK-AWGN (soft: LLR = 2y/sigma^2,
     positive favours 1; unquantized: y).  Returns (msgs, channel_values)."""
     msgs = rs.randint(0, 2, (batch, nbits))
-    coded = np.stack([conv_encode(m, trellis, termination) for m in msgs]).astype(np.float64)
+    coded = encode_batch(msgs, trellis, termination).astype(np.float64)
     rate = trellis.k / trellis.n
     if mode == "hard":
         x = np.abs(coded - (rs.rand(*coded.shape) < flip))

@@ -140,3 +140,13 @@ def test_ldpc_design_loader(tmp_path):
     cols = np.concatenate([adj[i, :deg[i]] for i in range(n_c)])
     H2 = sp.csc_matrix((np.ones(len(rows), np.int8), (rows, cols)), shape=(12, 24)).toarray()
     assert np.array_equal(H2, H)
+
+
+def test_batch_encoder_helper_matches_conv_encode():
+    rs = np.random.RandomState(9)
+    for tr in helpers.reference_test_trellises() + [helpers.k7(), helpers.rsc_k4()]:
+        for term in ("cont", "term"):
+            msgs = rs.randint(0, 2, (5, 24 * tr.k))
+            got = helpers.encode_batch(msgs, tr, term)
+            for b in range(5):
+                assert np.array_equal(got[b], conv_encode(msgs[b], tr, term)), (tr.k, tr.n, term)
