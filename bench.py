@@ -43,7 +43,7 @@ class ViterbiWorkload:
         self.dtype = "u8" if mode == "hard" else "int32 fixed-point metrics (f32 LLR in)"
         # coded values in + decoded bits out, u8 bits / f32 soft values
         self.alg_bytes = self.n_in * (1 if mode == "hard" else 4) + nbits
-        self.kernel = "viterbi_fast_kernel<FFCode<6,0133,0171>,%d>" % (2 if mode == "hard" else 1)
+        self.kernel = "viterbi_fast_kernel_%s<FFCode<6,0133,0171>>" % ("hard" if mode == "hard" else "soft")
 
     def describe(self):
         d = {"workload": self.name, "code": "K=7 (0o133,0o171) rate 1/2, 'cont'", "info_bits": self.nbits,

@@ -86,16 +86,20 @@ namespace fast {
 constexpr int TBB = 16;            // windows per traceback block
 constexpr int QBITS = 19;          // |quantised LLR| <= 2^19
 constexpr int QMAX = 1 << QBITS;
+constexpr int BD = 32;             // one warp per CTA: every synchronisation below is a __syncwarp()
+constexpr int QD = 4;              // input prefetch distance, in pairs of trellis steps
 
 struct Params {
     const void *coded;
     int64_t n_in;
     int64_t batch;
     int L, T, D, R;
-    int mode;                // CPB_VITERBI_*
+    int mode;                    // CPB_VITERBI_*
     const uint32_t *amax_bits;   // float input: bits of max |x| over the call (device)
     uint8_t *out;
-    int out_vec16;           // 1: rows of out are 16-byte aligned
+    int out_vec16;               // 1: rows of out are 16-byte aligned
+    int in_aligned;              // 1: rows of coded are 4-byte (u8) / 16-byte (f32) aligned and n_in % 4 == 0
+    uint32_t keep_mask;          // ~IDX_MASK, passed at run time so the key fix-up stays one LOP3 (reg & reg | imm)
 };
 
 template <int PACK> struct KeyOps;
@@ -119,7 +123,7 @@ template <> struct KeyOps<1> {
 // one trellis step on register-resident keys: Kn <- ACS(K, Bm); W <- survivor bits; returns min key(s)
 template <class CODE, int PACK>
 __device__ __forceinline__ uint32_t acs_step(const uint32_t (&K)[64], uint32_t (&Kn)[64], const uint32_t (&Bm)[4],
-                                             uint32_t (&W)[2 * PACK])
+                                             uint32_t (&W)[2 * PACK], const uint32_t keep)
 {
     using OPS = KeyOps<PACK>;
     constexpr int H = CODE::S / 2;
@@ -128,13 +132,15 @@ __device__ __forceinline__ uint32_t acs_step(const uint32_t (&K)[64], uint32_t (
     for (int w = 0; w < 2 * PACK; ++w) W[w] = 0;
 #pragma unroll
     for (int l = 0; l < H; ++l) {
-        // predecessors 2l (survivor bit 0) and 2l+1 (bit 1); new state l <- input 0, l+H <- input 1
+        // predecessors 2l (survivor bit 0) and 2l+1 (bit 1); new state l <- input 0, l+H <- input 1.
+        // keys are metric*64 + state: the smaller key wins, ties go to predecessor 2l (convcode.py:612-642),
+        // and the winner's LSB is the survivor bit.
         const uint32_t c10 = K[2 * l + 1] + Bm[CODE::out(2 * l + 1, 0)];
         const uint32_t m0 = OPS::addmin(K[2 * l], Bm[CODE::out(2 * l, 0)], c10);
         const uint32_t c11 = K[2 * l + 1] + Bm[CODE::out(2 * l + 1, 1)];
         const uint32_t m1 = OPS::addmin(K[2 * l], Bm[CODE::out(2 * l, 1)], c11);
-        Kn[l] = (m0 & ~OPS::IDX_MASK) | OPS::idx(l);
-        Kn[l + H] = (m1 & ~OPS::IDX_MASK) | OPS::idx(l + H);
+        Kn[l] = (m0 & keep) | OPS::idx(l);
+        Kn[l + H] = (m1 & keep) | OPS::idx(l + H);
         W[l >> WSH] += (m0 & OPS::LSB) << (l & ((1 << WSH) - 1));
         W[(l + H) >> WSH] += (m1 & OPS::LSB) << (l & ((1 << WSH) - 1));
     }
@@ -152,72 +158,122 @@ __device__ __forceinline__ uint32_t acs_step(const uint32_t (&K)[64], uint32_t (
     return OPS::min3(a, b, OPS::min2(q[6], q[7]));
 }
 
-// shared-memory survivor ring, thread-private columns: words [slot][w][tid], best [slot][tid]
+// shared memory of one warp-CTA
 template <int PACK>
-struct Ring {
-    uint32_t *w;
-    uint16_t *best;
-    int bd, tid, R;
-    __device__ __forceinline__ void store(int slot, const uint32_t (&W)[2 * PACK], uint32_t bestv)
+struct Smem {
+    uint32_t *w;        // survivor ring [R][2*PACK][32]
+    uint16_t *best;     // best states   [R][32]   (frame B in the high byte)
+    uint4 *lut;         // hard-decision branch metrics [16]
+    uint32_t *tasks;    // traceback tasks [17*32*PACK]
+    uint32_t *ntasks;   // [1]
+    uint32_t *outbits;  // [32*PACK][2]
+    int R;
+    __device__ __forceinline__ int get_best(int slot, int col, int fi) const { return (best[slot * BD + col] >> (8 * fi)) & 63; }
+    __device__ __forceinline__ int get_dec(int slot, int col, int s, int fi) const
     {
-#pragma unroll
-        for (int i = 0; i < 2 * PACK; ++i) w[(slot * 2 * PACK + i) * bd + tid] = W[i];
-        best[slot * bd + tid] = (uint16_t)bestv;
-    }
-    __device__ __forceinline__ int get_best(int slot, int fi) const { return (best[slot * bd + tid] >> (8 * fi)) & 63; }
-    __device__ __forceinline__ int get_dec(int slot, int s, int fi) const
-    {
-        if (PACK == 2) return (w[(slot * 4 + (s >> 4)) * bd + tid] >> ((s & 15) + 16 * fi)) & 1;
-        return (w[(slot * 2 + (s >> 5)) * bd + tid] >> (s & 31)) & 1;
+        if (PACK == 2) return (w[(slot * 4 + (s >> 4)) * BD + col] >> ((s & 15) + 16 * fi)) & 1;
+        return (w[(slot * 2 + (s >> 5)) * BD + col] >> (s & 31)) & 1;
     }
     __device__ __forceinline__ int dec_slot(int slot) const { return slot == 0 ? R - 1 : slot - 1; }
 };
 
-// Traceback for the windows t' in (ts, te].  slot_te = ring slot of step te.
-// Bit p (0-based) of the frame is the input of step q = p+1; on a path whose state at step tau is s,
-// that input is bit (tau - q) of ... the state holds the last M inputs, newest in the MSB, so the input of
-// step tau-(M-1) is the LSB of s (App. A.1-9).
+static size_t smem_bytes(int R, int pack)
+{
+    size_t b = (size_t)R * 2 * pack * BD * sizeof(uint32_t);
+    b += (((size_t)R * BD * sizeof(uint16_t)) + 15) & ~(size_t)15;
+    b += 16 * sizeof(uint4);
+    b += (size_t)17 * BD * pack * sizeof(uint32_t) + 16;
+    b += (size_t)BD * pack * 2 * sizeof(uint32_t);
+    return b;
+}
+
+// Traceback of the windows t' in (ts, te] (App. A.1-8): bit p of the frame is the input of step q = p+1 read on
+// the survivor path that starts at best[min(q + D - 2, T)].  The state holds the last M inputs, so the input of
+// step tau-(M-1) is the LSB of the path's state at step tau.
+//   phase A  every thread walks tau = te .. ts+1 once along the current path of each of its frames; where the
+//            path misses best[tau] it is retired into a task (it still owes the bits of the windows (tau, hi] it
+//            served) and a new path starts at best[tau].  16 iterations, no divergence.
+//   phase B  each task walks D-2-(M-1) further steps and emits its bits.  All tasks have the same length and any
+//            lane can run any task (the ring is in shared memory), so the warp shares them evenly -- the cost
+//            follows the AVERAGE number of survivor-path switches per frame, not the worst lane.
 template <class CODE, int PACK>
-__device__ __forceinline__ void tb_block(const Ring<PACK> &ring, int ts, int te, bool final_blk, int slot_te, int D,
-                                         int L, uint8_t *const (&outp)[PACK], const bool (&valid)[PACK], int out_vec16)
+__device__ __noinline__ void tb_block(const Smem<PACK> sm, int ts, int te, int final_blk, int slot_te, int D, int L,
+                                      uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec16)
 {
     constexpr int M = CODE::M, S = CODE::S;
-    const int p0 = ts - D + 2;                 // first bit of this block
-    const int tau_min = ts - D + 3 + (M - 1);
-    const int q_hi = final_blk ? te : te - D + 2;
+    const int lane = threadIdx.x;
+    const int p0 = ts - D + 2;                     // first bit of this block
+    const int wofs = D - 2 - (M - 1);              // window served by the LSB read at step tau: tau + wofs
+    unsigned long long acc[PACK];
+    int hi[PACK], s[PACK];
+    if (lane == 0) *sm.ntasks = BD * PACK;         // slots [0, 32*PACK) are the per-frame closing tasks
 #pragma unroll
     for (int fi = 0; fi < PACK; ++fi) {
-        unsigned long long acc = 0ull;
-        uint32_t cons = 0;
-        int s = ring.get_best(slot_te, fi);
-        int slot = slot_te;
-        for (int tau = te; tau >= tau_min; --tau) {
-            if (tau > ts) cons |= (uint32_t)(s == ring.get_best(slot, fi)) << (tau - ts - 1);
-            const int q = tau - (M - 1);
-            if (q >= 1 && q <= q_hi) acc |= (unsigned long long)(s & 1) << (q - 1 - p0);
-            s = ((s << 1) & (S - 1)) | ring.get_dec(slot, s, fi);
-            slot = ring.dec_slot(slot);
-        }
-        // windows whose own best state is not on the long path: individual (D-1)-step traceback
-        const int nwin = te - ts;
-        uint32_t todo = ~cons & ((nwin >= 32) ? 0xffffffffu : ((1u << nwin) - 1u));
-        while (todo) {
-            const int j = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int tp = ts + 1 + j;
-            int sl = slot_te - (te - tp);
-            if (sl < 0) sl += ring.R;
-            int s2 = ring.get_best(sl, fi);
-            for (int i = 0; i < D - 2 - (M - 1); ++i) {
-                s2 = ((s2 << 1) & (S - 1)) | ring.get_dec(sl, s2, fi);
-                sl = ring.dec_slot(sl);
+        acc[fi] = 0ull; hi[fi] = te; s[fi] = sm.get_best(slot_te, lane, fi);
+        sm.outbits[(lane + BD * fi) * 2] = 0u; sm.outbits[(lane + BD * fi) * 2 + 1] = 0u;
+    }
+    __syncwarp();
+    const bool emit_a = final_blk || (wofs < TBB);
+    int slot = slot_te;
+    for (int tau = te; tau > ts; --tau) {
+        const uint32_t bw = sm.best[slot * BD + lane];
+#pragma unroll
+        for (int fi = 0; fi < PACK; ++fi) {
+            const int b = (bw >> (8 * fi)) & 63;
+            if (tau < hi[fi] && s[fi] != b) {
+                const uint32_t slotq = atomicAdd(sm.ntasks, 1u);
+                sm.tasks[slotq] = (uint32_t)lane | ((uint32_t)fi << 5) | ((uint32_t)s[fi] << 6) |
+                                  ((uint32_t)(tau - ts) << 12) | ((uint32_t)(hi[fi] - ts) << 17);
+                hi[fi] = tau;
+                s[fi] = b;
             }
-            acc = (acc & ~(1ull << j)) | ((unsigned long long)(s2 & 1) << j);
+            if (emit_a) {
+                const int q = tau - (M - 1);
+                int w = tau + wofs;
+                if (final_blk && w > te) w = te;
+                if (q >= 1 && w <= hi[fi]) acc[fi] |= (unsigned long long)(s[fi] & 1) << (q - 1 - p0);
+            }
+            s[fi] = ((s[fi] << 1) & (S - 1)) | sm.get_dec(slot, lane, s[fi], fi);
         }
-        if (!valid[fi]) continue;
-        uint8_t *o = outp[fi] + p0;
+        slot = sm.dec_slot(slot);
+    }
+#pragma unroll
+    for (int fi = 0; fi < PACK; ++fi)
+        sm.tasks[lane + BD * fi] = (uint32_t)lane | ((uint32_t)fi << 5) | ((uint32_t)s[fi] << 6) |
+                                   ((uint32_t)(hi[fi] - ts) << 17);            // closing task: tau_b = ts
+    __syncwarp();
+    const int ntasks = (int)*sm.ntasks;
+    int slot_ts = slot_te - (te - ts);
+    if (slot_ts < 0) slot_ts += sm.R;
+    for (int i = lane; i < ntasks; i += BD) {
+        const uint32_t tk = sm.tasks[i];
+        const int col = tk & 31, fi = (tk >> 5) & 1;
+        int st = (tk >> 6) & 63;
+        const int tb = ts + (int)((tk >> 12) & 31), thi = ts + (int)((tk >> 17) & 31);
+        int sl = slot_ts + (tb - ts);
+        if (sl >= sm.R) sl -= sm.R;
+        unsigned long long bits = 0ull;
+        for (int tau = tb; tau > tb - wofs; --tau) {
+            const int q = tau - (M - 1);
+            int w = tau + wofs;
+            if (final_blk && w > te) w = te;
+            if (q >= 1 && w > tb && w <= thi) bits |= (unsigned long long)(st & 1) << (q - 1 - p0);
+            st = ((st << 1) & (S - 1)) | sm.get_dec(sl, col, st, fi);
+            sl = sm.dec_slot(sl);
+        }
+        const uint32_t blo = (uint32_t)bits, bhi = (uint32_t)(bits >> 32);
+        if (blo) atomicOr(&sm.outbits[(col + BD * fi) * 2], blo);
+        if (bhi) atomicOr(&sm.outbits[(col + BD * fi) * 2 + 1], bhi);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int fi = 0; fi < PACK; ++fi) {
+        acc[fi] |= (unsigned long long)sm.outbits[(lane + BD * fi) * 2] |
+                   ((unsigned long long)sm.outbits[(lane + BD * fi) * 2 + 1] << 32);
+        if (!((valid_mask >> fi) & 1)) continue;
+        uint8_t *o = (fi == 0 ? out0 : out1) + p0;
         if (!final_blk && out_vec16) {
-            const uint32_t b16 = (uint32_t)acc & 0xffffu;
+            const uint32_t b16 = (uint32_t)acc[fi] & 0xffffu;
             uint4 v;
             v.x = (((b16 >> 0) & 15u) * 0x00204081u) & 0x01010101u;
             v.y = (((b16 >> 4) & 15u) * 0x00204081u) & 0x01010101u;
@@ -226,25 +282,31 @@ __device__ __forceinline__ void tb_block(const Ring<PACK> &ring, int ts, int te,
             *reinterpret_cast<uint4 *>(o) = v;
         } else {
             const int cnt = final_blk ? (L - p0) : TBB;
-            for (int i = 0; i < cnt; ++i) o[i] = (uint8_t)((acc >> i) & 1ull);
+            for (int i = 0; i < cnt; ++i) o[i] = (uint8_t)((acc[fi] >> i) & 1ull);
         }
     }
+    __syncwarp();
 }
 
 template <class CODE, int PACK>
-__global__ void __launch_bounds__(128) viterbi_fast_kernel(const Params p)
+__device__ __forceinline__ void viterbi_fast_body(const Params &p)
 {
     using OPS = KeyOps<PACK>;
     constexpr int S = CODE::S, M = CODE::M;
     static_assert(S == 64, "fast path is written for 64 states");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int bd = blockDim.x, tid = threadIdx.x;
-    Ring<PACK> ring;
-    ring.bd = bd; ring.tid = tid; ring.R = p.R;
-    ring.w = reinterpret_cast<uint32_t *>(smem_raw);
-    ring.best = reinterpret_cast<uint16_t *>(smem_raw + (size_t)p.R * 2 * PACK * bd * sizeof(uint32_t));
-    uint4 *lut = reinterpret_cast<uint4 *>(smem_raw + (size_t)p.R * 2 * PACK * bd * sizeof(uint32_t) +
-                                           (((size_t)p.R * bd * sizeof(uint16_t) + 15) & ~(size_t)15));
+    const int tid = threadIdx.x;
+    Smem<PACK> sm;
+    {
+        unsigned char *q = smem_raw;
+        sm.R = p.R;
+        sm.w = reinterpret_cast<uint32_t *>(q); q += (size_t)p.R * 2 * PACK * BD * sizeof(uint32_t);
+        sm.best = reinterpret_cast<uint16_t *>(q); q += (((size_t)p.R * BD * sizeof(uint16_t)) + 15) & ~(size_t)15;
+        sm.lut = reinterpret_cast<uint4 *>(q); q += 16 * sizeof(uint4);
+        sm.tasks = reinterpret_cast<uint32_t *>(q); q += (size_t)17 * BD * PACK * sizeof(uint32_t);
+        sm.ntasks = reinterpret_cast<uint32_t *>(q); q += 16;
+        sm.outbits = reinterpret_cast<uint32_t *>(q);
+    }
     if (PACK == 2) {
         // hard-decision branch metrics of two frames: entry idx = r0A | r1A<<1 | r0B<<2 | r1B<<3,
         // component o = Hamming distance to output symbol o (convcode.py:579), times 64, frame B in the high half
@@ -252,21 +314,20 @@ __global__ void __launch_bounds__(128) viterbi_fast_kernel(const Params p)
             const int a = ((tid & 1) << 1) | ((tid >> 1) & 1), b = (((tid >> 2) & 1) << 1) | ((tid >> 3) & 1);
             uint32_t e[4];
             for (int o = 0; o < 4; ++o) e[o] = ((uint32_t)__popc(o ^ a) << 6) | ((uint32_t)__popc(o ^ b) << 22);
-            lut[tid] = make_uint4(e[0], e[1], e[2], e[3]);
+            sm.lut[tid] = make_uint4(e[0], e[1], e[2], e[3]);
         }
-        __syncthreads();
+        __syncwarp();
     }
 
-    // frames of this thread
-    const int64_t base = (int64_t)blockIdx.x * bd * PACK;
+    // frames of this thread (frame B = frame A + 32)
+    const int64_t base = (int64_t)blockIdx.x * BD * PACK;
     int64_t fr[PACK];
-    bool valid[PACK];
-    uint8_t *outp[PACK];
+    int valid_mask = 0;
+    uint8_t *outp[2] = {nullptr, nullptr};
 #pragma unroll
     for (int fi = 0; fi < PACK; ++fi) {
-        fr[fi] = base + (int64_t)fi * bd + tid;
-        valid[fi] = fr[fi] < p.batch;
-        if (!valid[fi]) fr[fi] = p.batch - 1;
+        fr[fi] = base + (int64_t)fi * BD + tid;
+        if (fr[fi] < p.batch) valid_mask |= 1 << fi; else fr[fi] = p.batch - 1;
         outp[fi] = p.out + fr[fi] * (int64_t)p.L;
     }
 
@@ -292,44 +353,64 @@ __global__ void __launch_bounds__(128) viterbi_fast_kernel(const Params p)
             K[s] = (PACK == 2) ? ((v | (v << 16)) | OPS::idx(s)) : (v | OPS::idx(s));
         }
     }
+    const uint32_t keep = p.keep_mask;
 
     const unsigned char *c8 = reinterpret_cast<const unsigned char *>(p.coded);
     const float *cf = reinterpret_cast<const float *>(p.coded);
+    const int npairs_in = p.L >> 1;              // pairs of steps fully covered by received data (aligned path)
 
-    // received pair of step tau -> the four branch metrics Bm[o] (times 64)
-    auto load_raw = [&](int tau, uint32_t &ra, uint32_t &rb) {
-        // hard: ra = idx bits for frame A/B ; float: ra, rb = bits of r0, r1
+    // raw received values of the pair of steps (2*pr+1, 2*pr+2)
+    struct Raw { uint32_t a, b, c, d; };
+    auto load_pair = [&](int pr) {
+        Raw r;
         if (PACK == 2) {
-            uint32_t idx = 0;
-            if (tau <= p.L) {
+            r.a = r.b = r.c = r.d = 0u;
+            if (p.in_aligned) {
+                if (pr < npairs_in) {
+                    r.a = __ldg(reinterpret_cast<const uint32_t *>(c8 + fr[0] * p.n_in) + pr);
+                    r.b = __ldg(reinterpret_cast<const uint32_t *>(c8 + fr[PACK - 1] * p.n_in) + pr);
+                }
+            } else {
 #pragma unroll
-                for (int fi = 0; fi < PACK; ++fi) {
-                    const unsigned char *q = c8 + fr[fi] * p.n_in + 2 * (int64_t)(tau - 1);
-                    idx |= ((uint32_t)(__ldg(q) & 1u) | ((uint32_t)(__ldg(q + 1) & 1u) << 1)) << (2 * fi);
+                for (int h = 0; h < 2; ++h) {
+                    const int tau = 2 * pr + 1 + h;
+                    if (tau <= p.L) {
+                        const unsigned char *qa = c8 + fr[0] * p.n_in + 2 * (int64_t)(tau - 1);
+                        const unsigned char *qb = c8 + fr[PACK - 1] * p.n_in + 2 * (int64_t)(tau - 1);
+                        r.a |= ((uint32_t)__ldg(qa) | ((uint32_t)__ldg(qa + 1) << 8)) << (16 * h);
+                        r.b |= ((uint32_t)__ldg(qb) | ((uint32_t)__ldg(qb + 1) << 8)) << (16 * h);
+                    }
                 }
             }
-            ra = idx; rb = 0;
         } else {
-            float r0 = padq, r1 = padq;
-            if (tau <= p.L) {
-                const float *q = cf + fr[0] * p.n_in + 2 * (int64_t)(tau - 1);
-                r0 = __ldg(q); r1 = __ldg(q + 1);
+            const uint32_t pb = __float_as_uint(padq);
+            r.a = r.b = r.c = r.d = pb;
+            const float *row = cf + fr[0] * p.n_in;
+            if (p.in_aligned && pr < npairs_in) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(row) + pr);
+                r.a = __float_as_uint(v.x); r.b = __float_as_uint(v.y); r.c = __float_as_uint(v.z); r.d = __float_as_uint(v.w);
+            } else if (!p.in_aligned) {
+                const int tau = 2 * pr + 1;
+                if (tau <= p.L) { r.a = __float_as_uint(__ldg(row + 2 * (tau - 1))); r.b = __float_as_uint(__ldg(row + 2 * (tau - 1) + 1)); }
+                if (tau + 1 <= p.L) { r.c = __float_as_uint(__ldg(row + 2 * tau)); r.d = __float_as_uint(__ldg(row + 2 * tau + 1)); }
             }
-            ra = __float_as_uint(r0); rb = __float_as_uint(r1);
         }
+        return r;
     };
-    auto make_bm = [&](uint32_t ra, uint32_t rb, uint32_t (&Bm)[4]) {
+    // the four branch metrics (times 64) of step h (0/1) of a pair
+    auto make_bm = [&](const Raw &r, int h, uint32_t (&Bm)[4]) {
         if (PACK == 2) {
-            const uint4 e = lut[ra];
+            const uint32_t ta = (r.a | (r.a >> 7)) >> (16 * h), tb = (r.b | (r.b >> 7)) >> (16 * h);
+            const uint4 e = sm.lut[(ta & 3u) | ((tb & 3u) << 2)];
             Bm[0] = e.x; Bm[1] = e.y; Bm[2] = e.z; Bm[3] = e.w;
         } else {
-            float r0 = __uint_as_float(ra), r1 = __uint_as_float(rb);
+            float r0 = __uint_as_float(h ? r.c : r.a), r1 = __uint_as_float(h ? r.d : r.b);
             if (p.mode == CPB_VITERBI_SOFT) {          // convcode.py:718-719
                 r0 = fminf(fmaxf(r0, -500.0f), 500.0f);
                 r1 = fminf(fmaxf(r1, -500.0f), 500.0f);
             }
-            int q0 = __float2int_rn(fminf(fmaxf(r0 * scale, -(float)QMAX), (float)QMAX));
-            int q1 = __float2int_rn(fminf(fmaxf(r1 * scale, -(float)QMAX), (float)QMAX));
+            const int q0 = __float2int_rn(fminf(fmaxf(r0 * scale, -(float)QMAX), (float)QMAX));
+            const int q1 = __float2int_rn(fminf(fmaxf(r1 * scale, -(float)QMAX), (float)QMAX));
             // -log-likelihood of code bit c given value r, up to a per-step constant (convcode.py:581-587):
             // c = 0 costs max(q,0), c = 1 costs max(-q,0)
             const uint32_t z0 = (uint32_t)max(q0, 0) << 6, o0 = (uint32_t)max(-q0, 0) << 6;
@@ -344,40 +425,50 @@ __global__ void __launch_bounds__(128) viterbi_fast_kernel(const Params p)
 
     auto finish_step = [&](int tau, uint32_t mn, uint32_t (&Kc)[64]) {
         const uint32_t bestv = (PACK == 2) ? ((mn & 63u) | (((mn >> 16) & 63u) << 8)) : (mn & 63u);
-        ring.store(slot, W, bestv);
+#pragma unroll
+        for (int i = 0; i < 2 * PACK; ++i) sm.w[(slot * 2 * PACK + i) * BD + tid] = W[i];
+        sm.best[slot * BD + tid] = (uint16_t)bestv;
         if ((tau & 15) == 0) {          // renormalise: subtract the minimum metric from every key
             const uint32_t sub = mn & ~OPS::IDX_MASK;
 #pragma unroll
             for (int s = 0; s < 64; ++s) Kc[s] -= sub;
         }
-        if (tau == p.T) {
-            tb_block<CODE, PACK>(ring, next_te - TBB, tau, true, slot, p.D, p.L, outp, valid, p.out_vec16);
-        } else if (tau == next_te) {
-            tb_block<CODE, PACK>(ring, next_te - TBB, tau, false, slot, p.D, p.L, outp, valid, p.out_vec16);
+        if (tau == p.T || tau == next_te) {
+            const int fin = (tau == p.T) ? 1 : 0;
+            tb_block<CODE, PACK>(sm, next_te - TBB, tau, fin, slot, p.D, p.L, outp[0], outp[PACK - 1], valid_mask, p.out_vec16);
             next_te += TBB;
         }
         slot = (slot + 1 == p.R) ? 0 : slot + 1;
     };
 
-    uint32_t ra0, rb0, ra1, rb1;
-    load_raw(1, ra0, rb0);
-    load_raw(2, ra1, rb1);
-    for (int tau = 1; tau <= p.T; tau += 2) {
-        uint32_t na0, nb0, na1, nb1;
-        load_raw(tau + 2, na0, nb0);      // software prefetch of the next pair of steps
-        load_raw(tau + 3, na1, nb1);
+    Raw qd[QD];
+#pragma unroll
+    for (int i = 0; i < QD; ++i) qd[i] = load_pair(i);
+    const int npairs = (p.T + 1) >> 1;
+    for (int pr = 0; pr < npairs; ++pr) {
+        const Raw cur = qd[0];
+#pragma unroll
+        for (int i = 0; i + 1 < QD; ++i) qd[i] = qd[i + 1];
+        qd[QD - 1] = load_pair(pr + QD);            // software prefetch, QD pairs of steps ahead
+        const int tau = 2 * pr + 1;
         uint32_t Bm[4];
-        make_bm(ra0, rb0, Bm);
-        uint32_t mn = acs_step<CODE, PACK>(K, Kn, Bm, W);
+        make_bm(cur, 0, Bm);
+        uint32_t mn = acs_step<CODE, PACK>(K, Kn, Bm, W, keep);
         finish_step(tau, mn, Kn);
         if (tau + 1 <= p.T) {
-            make_bm(ra1, rb1, Bm);
-            mn = acs_step<CODE, PACK>(Kn, K, Bm, W);
+            make_bm(cur, 1, Bm);
+            mn = acs_step<CODE, PACK>(Kn, K, Bm, W, keep);
             finish_step(tau + 1, mn, K);
         }
-        ra0 = na0; rb0 = nb0; ra1 = na1; rb1 = nb1;
     }
 }
+
+// hard decision: two u16x2-packed frames per thread (213 registers, 7-8 warps per SM)
+template <class CODE>
+__global__ void __launch_bounds__(BD) viterbi_fast_kernel_hard(const Params p) { viterbi_fast_body<CODE, 2>(p); }
+// soft / unquantized: one frame per thread, capped at 168 registers so that 12 warps fit an SM
+template <class CODE>
+__global__ void __launch_bounds__(BD, 12) viterbi_fast_kernel_soft(const Params p) { viterbi_fast_body<CODE, 1>(p); }
 
 // max |x| over a float buffer, as uint bits (non-negative floats order like unsigned ints)
 __global__ void absmax_kernel(const float *__restrict__ x, int64_t n, int clip500, uint32_t *out_bits)
@@ -393,21 +484,14 @@ __global__ void absmax_kernel(const float *__restrict__ x, int64_t n, int clip50
     if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));
 }
 
-static size_t smem_bytes(int R, int bd, int pack)
-{
-    size_t ring_w = (size_t)R * 2 * pack * bd * sizeof(uint32_t);
-    size_t ring_b = (((size_t)R * bd * sizeof(uint16_t)) + 15) & ~(size_t)15;
-    return ring_w + ring_b + 16 * sizeof(uint4);
-}
-
 template <class CODE, int PACK>
-static int launch(const Params &p, int bd, cudaStream_t st)
+static int launch(const Params &p, cudaStream_t st)
 {
-    const size_t smem = smem_bytes(p.R, bd, PACK);
-    auto kern = viterbi_fast_kernel<CODE, PACK>;
+    const size_t smem = smem_bytes(p.R, PACK);
+    void (*kern)(const Params) = (PACK == 2) ? viterbi_fast_kernel_hard<CODE> : viterbi_fast_kernel_soft<CODE>;
     CPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t grid = ceil_div(p.batch, (int64_t)bd * PACK);
-    kern<<<(unsigned)grid, bd, smem, st>>>(p);
+    const int64_t grid = ceil_div(p.batch, (int64_t)BD * PACK);
+    kern<<<(unsigned)grid, BD, smem, st>>>(p);
     CPB_LAUNCH_CHECK();
     return CPB_OK;
 }
@@ -695,8 +779,12 @@ int cpb_viterbi_decode(const cpbTrellis *t, const void *coded_dev, int in_dtype,
         int rc = ws.acquire(workspace_dev, workspace_bytes, 256, st);
         if (rc) return rc;
         const int pack = (mode == CPB_VITERBI_HARD) ? 2 : 1;
-        int bd = 32;
-        if (fast::smem_bytes(p.R, bd, pack) > dp.smem_optin) { ws.release(); return CPB_EUNSUPPORTED; }
+        if (fast::smem_bytes(p.R, pack) > dp.smem_optin) { ws.release(); return CPB_EUNSUPPORTED; }
+        p.keep_mask = (pack == 2) ? ~fast::KeyOps<2>::IDX_MASK : ~fast::KeyOps<1>::IDX_MASK;
+        {
+            const size_t row = (size_t)n_in * (pack == 2 ? 1 : 4), al = (pack == 2) ? 4 : 16;
+            p.in_aligned = ((n_in % 4) == 0 && (row % al) == 0 && (((uintptr_t)coded_dev) % al) == 0) ? 1 : 0;
+        }
         if (pack == 1) {
             p.amax_bits = reinterpret_cast<const uint32_t *>(ws.ptr);
             cudaError_t e = cudaMemsetAsync(ws.ptr, 0, 4, st);
@@ -708,13 +796,13 @@ int cpb_viterbi_decode(const cpbTrellis *t, const void *coded_dev, int in_dtype,
                                                     mode == CPB_VITERBI_SOFT, reinterpret_cast<uint32_t *>(ws.ptr));
         }
         if (pack == 2) {
-            if (t->fast_id == 1) rc = fast::launch<Code133_171, 2>(p, bd, st);
-            else if (t->fast_id == 2) rc = fast::launch<Code171_133, 2>(p, bd, st);
-            else rc = fast::launch<Code5_43, 2>(p, bd, st);
+            if (t->fast_id == 1) rc = fast::launch<Code133_171, 2>(p, st);
+            else if (t->fast_id == 2) rc = fast::launch<Code171_133, 2>(p, st);
+            else rc = fast::launch<Code5_43, 2>(p, st);
         } else {
-            if (t->fast_id == 1) rc = fast::launch<Code133_171, 1>(p, bd, st);
-            else if (t->fast_id == 2) rc = fast::launch<Code171_133, 1>(p, bd, st);
-            else rc = fast::launch<Code5_43, 1>(p, bd, st);
+            if (t->fast_id == 1) rc = fast::launch<Code133_171, 1>(p, st);
+            else if (t->fast_id == 2) rc = fast::launch<Code171_133, 1>(p, st);
+            else rc = fast::launch<Code5_43, 1>(p, st);
         }
         ws.release();
         return rc;

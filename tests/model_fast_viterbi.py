@@ -42,34 +42,45 @@ def decode(coded, G0, G1, D=None, mode="hard", qmax=1 << 19, M=6, stats=None):
     next_te = D - 2 + TBB
 
     def tb_block(ts, te, final, slot_te):
+        """Two-phase traceback (what viterbi_fast_kernel does):
+        phase A  walk tau = te .. ts+1 once, following the current path; whenever the path's state differs from
+                 best[tau] the current path is retired into a TASK (it still owes the bits of the windows it
+                 served) and a new path starts from best[tau];
+        phase B  every task walks D-7 further steps (equal length -> lanes of a warp share them evenly) and
+                 emits the input bits of its windows (lo, hi]."""
         p0 = ts - D + 2
-        tau_min = ts - D + 3 + (M - 1)
-        q_hi = te if final else te - D + 2
         acc = {}
-        cons = 0
-        s = int(ring_b[slot_te])
+        tasks = []
+
+        def wclamp(tau):
+            w = tau + D - 2 - (M - 1)
+            return te if (final and w > te) else w
+
+        hi = te
         sl = slot_te
-        for tau in range(te, tau_min - 1, -1):
-            if tau > ts and s == int(ring_b[sl]):
-                cons |= 1 << (tau - ts - 1)
+        s = int(ring_b[sl])
+        for tau in range(te, ts, -1):
+            if tau < hi and s != int(ring_b[sl]):
+                tasks.append((tau, s, sl, tau, hi))          # retire: (tau_b, state at tau_b, slot, lo, hi)
+                hi = tau
+                s = int(ring_b[sl])
             q = tau - (M - 1)
-            if 1 <= q <= q_hi:
+            if q >= 1 and wclamp(tau) <= hi:
                 acc[q - 1 - p0] = s & 1
             s = ((s << 1) & (S - 1)) | int(ring_w[sl, s])
             sl = R - 1 if sl == 0 else sl - 1
-        nwin = te - ts
-        for j in range(nwin):
-            if (cons >> j) & 1:
-                continue
-            if stats is not None:
-                stats["fallback"] = stats.get("fallback", 0) + 1
-            tp = ts + 1 + j
-            sl = (slot_te - (te - tp)) % R
-            s2 = int(ring_b[sl])
-            for _ in range(D - 2 - (M - 1)):
-                s2 = ((s2 << 1) & (S - 1)) | int(ring_w[sl, s2])
+        tasks.append((ts, s, sl, ts, hi))
+        if stats is not None:
+            stats["tasks"] = stats.get("tasks", 0) + len(tasks)
+            stats.setdefault("blocks", []).append(len(tasks))
+        for (tb, s, sl, lo, hi) in tasks:
+            for tau in range(tb, tb - (D - 2 - (M - 1)), -1):
+                q = tau - (M - 1)
+                w = wclamp(tau)
+                if q >= 1 and lo < w <= hi:
+                    acc[q - 1 - p0] = s & 1
+                s = ((s << 1) & (S - 1)) | int(ring_w[sl, s])
                 sl = R - 1 if sl == 0 else sl - 1
-            acc[j] = s2 & 1
         cnt = (L - p0) if final else TBB
         for i in range(cnt):
             out[p0 + i] = acc[i]
@@ -114,3 +125,4 @@ def decode(coded, G0, G1, D=None, mode="hard", qmax=1 << 19, M=6, stats=None):
         slot = 0 if slot + 1 == R else slot + 1
     assert (out >= 0).all()
     return out
+
