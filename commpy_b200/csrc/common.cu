@@ -25,6 +25,12 @@ const DeviceProps &device_props()
         cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev); p.cc_major = v;
         cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev); p.cc_minor = v;
         cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); p.smem_optin = (size_t)v;
+        // keep stream-ordered scratch cached in the default pool instead of returning it to the OS at every sync
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && pool) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
         size_t fr = 0, tot = 0;
         cudaMemGetInfo(&fr, &tot);
         p.global_mem = tot;

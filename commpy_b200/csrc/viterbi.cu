@@ -20,6 +20,7 @@
 // the long path does not pass through that window's own best state, which reproduces the reference's
 // per-step traceback bit for bit.
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -164,7 +165,7 @@ struct Smem {
     uint32_t *w;        // survivor ring [R][2*PACK][32]
     uint16_t *best;     // best states   [R][32]   (frame B in the high byte)
     uint4 *lut;         // hard-decision branch metrics [16]
-    uint32_t *tasks;    // traceback tasks [17*32*PACK]
+    uint32_t *tasks;    // retired-path tasks [2*TASK_CAP]
     uint32_t *ntasks;   // [1]
     uint32_t *outbits;  // [32*PACK][2]
     int R;
@@ -182,98 +183,158 @@ static size_t smem_bytes(int R, int pack)
     size_t b = (size_t)R * 2 * pack * BD * sizeof(uint32_t);
     b += (((size_t)R * BD * sizeof(uint16_t)) + 15) & ~(size_t)15;
     b += 16 * sizeof(uint4);
-    b += (size_t)17 * BD * pack * sizeof(uint32_t) + 16;
+    b += (size_t)2 * 384 * sizeof(uint32_t) + 16;
     b += (size_t)BD * pack * 2 * sizeof(uint32_t);
     return b;
 }
 
-// Traceback of the windows t' in (ts, te] (App. A.1-8): bit p of the frame is the input of step q = p+1 read on
-// the survivor path that starts at best[min(q + D - 2, T)].  The state holds the last M inputs, so the input of
-// step tau-(M-1) is the LSB of the path's state at step tau.
-//   phase A  every thread walks tau = te .. ts+1 once along the current path of each of its frames; where the
-//            path misses best[tau] it is retired into a task (it still owes the bits of the windows (tau, hi] it
-//            served) and a new path starts at best[tau].  16 iterations, no divergence.
-//   phase B  each task walks D-2-(M-1) further steps and emits its bits.  All tasks have the same length and any
-//            lane can run any task (the ring is in shared memory), so the warp shares them evenly -- the cost
+// Traceback of the windows t' in (ts, te] (App. A.1-8): bit p of the frame is the input u_{p+1} read on the
+// survivor path that starts at best[min(p + D - 1, T)].  A state holds the last M inputs (newest in the MSB), so a
+// walk just shifts survivor bits into a register: after k look-ups from step tau0 the low M bits of `path` are the
+// state at step tau0-k and bit b is u_{tau0-k-(M-1)+b}.
+//   phase A  every thread walks tau = te .. ts+1 once along the current path of each of its frames; where the path
+//            misses best[tau] it is retired into a task (it still owes the bits of the windows (tau, hi] it served)
+//            and a new path starts at best[tau].  16 iterations, no divergence.  The path alive at ts ("closing")
+//            is finished by its own thread.
+//   phase B  every retired path needs D-8 more look-ups.  All tasks have that same length and any lane can run any
+//            task (the ring is in shared memory), so the warp shares them evenly, two per lane at a time: the cost
 //            follows the AVERAGE number of survivor-path switches per frame, not the worst lane.
-template <class CODE, int PACK>
-__device__ __noinline__ void tb_block(const Smem<PACK> sm, int ts, int te, int final_blk, int slot_te, int D, int L,
+// A path that served the windows (lo, hi] and has been walked down to step lo-D+8 contributes
+//   (path << (lo-ts)) & bits[lo-ts, hi-ts)          (block bit j = window - ts - 1 = output bit p0 + j),
+// and in the final block the path started at T also owns every later bit up to L-1.
+template <int PACK, typename PT>
+struct Walker {
+    static constexpr int ROWB = 2 * PACK * BD * 4;      // bytes per ring slot
+    const unsigned char *wbase;
+    int rowoff, wrap;
+    int colsh, shbase;
+    PT path;
+    __device__ __forceinline__ void init(const Smem<PACK> &sm, int slot, int col, int fi, PT p0)
+    {
+        wbase = reinterpret_cast<const unsigned char *>(sm.w);
+        rowoff = slot * ROWB; wrap = sm.R * ROWB; colsh = col * 4; shbase = 16 * fi; path = p0;
+    }
+    __device__ __forceinline__ void step()              // survivor look-up at the current step, move one step back
+    {
+        const uint32_t st = (uint32_t)path & 63u;
+        const int sel = (PACK == 2) ? (int)((st << 3) & 0x180u) : (int)((st << 2) & 0x80u);   // word (st>>4 | st>>5) * 128 B
+        const uint32_t word = *reinterpret_cast<const uint32_t *>(wbase + rowoff + sel + colsh);
+        const uint32_t sh = (PACK == 2) ? ((st & 15u) | (uint32_t)shbase) : (st & 31u);
+        path = (path << 1) | (PT)((word >> sh) & 1u);
+        rowoff -= ROWB;
+        if (rowoff < 0) rowoff += wrap;
+    }
+    __device__ __forceinline__ uint32_t state() const { return (uint32_t)path & 63u; }
+};
+
+constexpr int TASK_CAP = 384;      // retired paths kept per block and warp; beyond that they are finished inline
+
+template <class CODE, int PACK, bool FINAL>
+__device__ __noinline__ void tb_block(const Smem<PACK> sm, int ts, int te, int slot_te, int D, int L,
                                       uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec16)
 {
-    constexpr int M = CODE::M, S = CODE::S;
+    using PT = typename std::conditional<FINAL, unsigned long long, uint32_t>::type;
+    constexpr int M = CODE::M;
     const int lane = threadIdx.x;
-    const int p0 = ts - D + 2;                     // first bit of this block
-    const int wofs = D - 2 - (M - 1);              // window served by the LSB read at step tau: tau + wofs
-    unsigned long long acc[PACK];
-    int hi[PACK], s[PACK];
-    if (lane == 0) *sm.ntasks = BD * PACK;         // slots [0, 32*PACK) are the per-frame closing tasks
+    const int p0 = ts - D + 2;                          // first output bit of this block
+    const int ext = (D - 2 - (M - 1) - 1 > 0) ? (D - 2 - (M - 1) - 1) : 0;     // look-ups below the window range
+    const int dsh = (D - 2 - (M - 1) - 1 < 0) ? 1 : 0;  // D = M+1: the walk is one look-up deeper than needed
+    auto contribution = [&](PT path, int lo, int hi) -> PT {
+        PT v = (PT)(path << (lo - ts)) >> dsh;
+        v &= (PT)(~(PT)0 << (lo - ts));
+        if (!(FINAL && hi == te)) v &= (PT) ~(PT)(~(PT)0 << (hi - ts));
+        return v;
+    };
+    if (lane == 0) *sm.ntasks = 0u;
+    PT acc[PACK];
+    int hi[PACK];
+    Walker<PACK, PT> wk[PACK];
 #pragma unroll
     for (int fi = 0; fi < PACK; ++fi) {
-        acc[fi] = 0ull; hi[fi] = te; s[fi] = sm.get_best(slot_te, lane, fi);
+        acc[fi] = 0; hi[fi] = te;
+        wk[fi].init(sm, slot_te, lane, fi, (PT)sm.get_best(slot_te, lane, fi));
         sm.outbits[(lane + BD * fi) * 2] = 0u; sm.outbits[(lane + BD * fi) * 2 + 1] = 0u;
     }
     __syncwarp();
-    const bool emit_a = final_blk || (wofs < TBB);
+    // ---- phase A
     int slot = slot_te;
     for (int tau = te; tau > ts; --tau) {
         const uint32_t bw = sm.best[slot * BD + lane];
 #pragma unroll
         for (int fi = 0; fi < PACK; ++fi) {
-            const int b = (bw >> (8 * fi)) & 63;
-            if (tau < hi[fi] && s[fi] != b) {
-                const uint32_t slotq = atomicAdd(sm.ntasks, 1u);
-                sm.tasks[slotq] = (uint32_t)lane | ((uint32_t)fi << 5) | ((uint32_t)s[fi] << 6) |
-                                  ((uint32_t)(tau - ts) << 12) | ((uint32_t)(hi[fi] - ts) << 17);
+            const uint32_t b = (bw >> (8 * fi)) & 63u;
+            if (tau < hi[fi] && wk[fi].state() != b) {          // the path does not pass through best[tau]: retire it
+                const uint32_t qi = atomicAdd(sm.ntasks, 1u);
+                if (qi < (uint32_t)TASK_CAP) {
+                    sm.tasks[2 * qi] = (uint32_t)lane | ((uint32_t)fi << 5) | ((uint32_t)(tau - ts) << 8) |
+                                       ((uint32_t)(hi[fi] - ts) << 16);
+                    sm.tasks[2 * qi + 1] = (uint32_t)wk[fi].path;      // <= 16 look-ups so far: fits 22 bits
+                } else {
+                    Walker<PACK, PT> t = wk[fi];
+                    for (int i = 0; i < ext; ++i) t.step();
+                    acc[fi] |= contribution(t.path, tau, hi[fi]);
+                }
                 hi[fi] = tau;
-                s[fi] = b;
+                wk[fi].path = (PT)b;
             }
-            if (emit_a) {
-                const int q = tau - (M - 1);
-                int w = tau + wofs;
-                if (final_blk && w > te) w = te;
-                if (q >= 1 && w <= hi[fi]) acc[fi] |= (unsigned long long)(s[fi] & 1) << (q - 1 - p0);
-            }
-            s[fi] = ((s[fi] << 1) & (S - 1)) | sm.get_dec(slot, lane, s[fi], fi);
+            wk[fi].step();
         }
         slot = sm.dec_slot(slot);
     }
+    // ---- closing paths of this thread's own frames (interleaved for ILP)
+    for (int i = 0; i < ext; ++i) {
 #pragma unroll
-    for (int fi = 0; fi < PACK; ++fi)
-        sm.tasks[lane + BD * fi] = (uint32_t)lane | ((uint32_t)fi << 5) | ((uint32_t)s[fi] << 6) |
-                                   ((uint32_t)(hi[fi] - ts) << 17);            // closing task: tau_b = ts
+        for (int fi = 0; fi < PACK; ++fi) wk[fi].step();
+    }
+#pragma unroll
+    for (int fi = 0; fi < PACK; ++fi) acc[fi] |= contribution(wk[fi].path, ts, hi[fi]);
     __syncwarp();
-    const int ntasks = (int)*sm.ntasks;
+    // ---- phase B: retired paths, two per lane at a time
+    int ntasks = (int)*sm.ntasks;
+    if (ntasks > TASK_CAP) ntasks = TASK_CAP;
     int slot_ts = slot_te - (te - ts);
     if (slot_ts < 0) slot_ts += sm.R;
-    for (int i = lane; i < ntasks; i += BD) {
-        const uint32_t tk = sm.tasks[i];
-        const int col = tk & 31, fi = (tk >> 5) & 1;
-        int st = (tk >> 6) & 63;
-        const int tb = ts + (int)((tk >> 12) & 31), thi = ts + (int)((tk >> 17) & 31);
-        int sl = slot_ts + (tb - ts);
-        if (sl >= sm.R) sl -= sm.R;
-        unsigned long long bits = 0ull;
-        for (int tau = tb; tau > tb - wofs; --tau) {
-            const int q = tau - (M - 1);
-            int w = tau + wofs;
-            if (final_blk && w > te) w = te;
-            if (q >= 1 && w > tb && w <= thi) bits |= (unsigned long long)(st & 1) << (q - 1 - p0);
-            st = ((st << 1) & (S - 1)) | sm.get_dec(sl, col, st, fi);
-            sl = sm.dec_slot(sl);
+    for (int base = 0; base < ntasks; base += 2 * BD) {
+        Walker<PACK, PT> tw[2];
+        int lo[2], thi[2], dst[2];
+        bool on[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = base + u * BD + lane;
+            on[u] = i < ntasks;
+            const uint32_t a = on[u] ? sm.tasks[2 * i] : 0u;
+            const int col = a & 31, fi = (a >> 5) & 1;
+            lo[u] = ts + (int)((a >> 8) & 255u); thi[u] = ts + (int)((a >> 16) & 255u);
+            dst[u] = (col + BD * fi) * 2;
+            int sl = slot_ts + (lo[u] - ts);             // the next look-up of a retired path is at step lo
+            if (sl >= sm.R) sl -= sm.R;
+            tw[u].init(sm, sl, col, fi, on[u] ? (PT)sm.tasks[2 * i + 1] : (PT)0);
         }
-        const uint32_t blo = (uint32_t)bits, bhi = (uint32_t)(bits >> 32);
-        if (blo) atomicOr(&sm.outbits[(col + BD * fi) * 2], blo);
-        if (bhi) atomicOr(&sm.outbits[(col + BD * fi) * 2 + 1], bhi);
+        for (int i = 0; i < ext; ++i) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) tw[u].step();
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!on[u]) continue;
+            const PT bits = contribution(tw[u].path, lo[u], thi[u]);
+            const uint32_t blo = (uint32_t)bits;
+            if (blo) atomicOr(&sm.outbits[dst[u]], blo);
+            if (FINAL) {
+                const uint32_t bhi = (uint32_t)((unsigned long long)bits >> 32);
+                if (bhi) atomicOr(&sm.outbits[dst[u] + 1], bhi);
+            }
+        }
     }
     __syncwarp();
 #pragma unroll
     for (int fi = 0; fi < PACK; ++fi) {
-        acc[fi] |= (unsigned long long)sm.outbits[(lane + BD * fi) * 2] |
-                   ((unsigned long long)sm.outbits[(lane + BD * fi) * 2 + 1] << 32);
+        unsigned long long a64 = (unsigned long long)acc[fi] | (unsigned long long)sm.outbits[(lane + BD * fi) * 2];
+        if (FINAL) a64 |= (unsigned long long)sm.outbits[(lane + BD * fi) * 2 + 1] << 32;
         if (!((valid_mask >> fi) & 1)) continue;
         uint8_t *o = (fi == 0 ? out0 : out1) + p0;
-        if (!final_blk && out_vec16) {
-            const uint32_t b16 = (uint32_t)acc[fi] & 0xffffu;
+        if (!FINAL && out_vec16 && te - ts == TBB) {
+            const uint32_t b16 = (uint32_t)a64 & 0xffffu;
             uint4 v;
             v.x = (((b16 >> 0) & 15u) * 0x00204081u) & 0x01010101u;
             v.y = (((b16 >> 4) & 15u) * 0x00204081u) & 0x01010101u;
@@ -281,8 +342,8 @@ __device__ __noinline__ void tb_block(const Smem<PACK> sm, int ts, int te, int f
             v.w = (((b16 >> 12) & 15u) * 0x00204081u) & 0x01010101u;
             *reinterpret_cast<uint4 *>(o) = v;
         } else {
-            const int cnt = final_blk ? (L - p0) : TBB;
-            for (int i = 0; i < cnt; ++i) o[i] = (uint8_t)((acc[fi] >> i) & 1ull);
+            const int cnt = FINAL ? (L - p0) : (te - ts);
+            for (int i = 0; i < cnt; ++i) o[i] = (uint8_t)((a64 >> i) & 1ull);
         }
     }
     __syncwarp();
@@ -303,7 +364,7 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
         sm.w = reinterpret_cast<uint32_t *>(q); q += (size_t)p.R * 2 * PACK * BD * sizeof(uint32_t);
         sm.best = reinterpret_cast<uint16_t *>(q); q += (((size_t)p.R * BD * sizeof(uint16_t)) + 15) & ~(size_t)15;
         sm.lut = reinterpret_cast<uint4 *>(q); q += 16 * sizeof(uint4);
-        sm.tasks = reinterpret_cast<uint32_t *>(q); q += (size_t)17 * BD * PACK * sizeof(uint32_t);
+        sm.tasks = reinterpret_cast<uint32_t *>(q); q += (size_t)2 * 384 * sizeof(uint32_t);
         sm.ntasks = reinterpret_cast<uint32_t *>(q); q += 16;
         sm.outbits = reinterpret_cast<uint32_t *>(q);
     }
@@ -433,9 +494,10 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
 #pragma unroll
             for (int s = 0; s < 64; ++s) Kc[s] -= sub;
         }
-        if (tau == p.T || tau == next_te) {
-            const int fin = (tau == p.T) ? 1 : 0;
-            tb_block<CODE, PACK>(sm, next_te - TBB, tau, fin, slot, p.D, p.L, outp[0], outp[PACK - 1], valid_mask, p.out_vec16);
+        if (tau == p.T) {
+            tb_block<CODE, PACK, true>(sm, next_te - TBB, tau, slot, p.D, p.L, outp[0], outp[PACK - 1], valid_mask, p.out_vec16);
+        } else if (tau == next_te) {
+            tb_block<CODE, PACK, false>(sm, next_te - TBB, tau, slot, p.D, p.L, outp[0], outp[PACK - 1], valid_mask, p.out_vec16);
             next_te += TBB;
         }
         slot = (slot + 1 == p.R) ? 0 : slot + 1;

@@ -42,48 +42,52 @@ def decode(coded, G0, G1, D=None, mode="hard", qmax=1 << 19, M=6, stats=None):
     next_te = D - 2 + TBB
 
     def tb_block(ts, te, final, slot_te):
-        """Two-phase traceback (what viterbi_fast_kernel does):
-        phase A  walk tau = te .. ts+1 once, following the current path; whenever the path's state differs from
-                 best[tau] the current path is retired into a TASK (it still owes the bits of the windows it
-                 served) and a new path starts from best[tau];
-        phase B  every task walks D-7 further steps (equal length -> lanes of a warp share them evenly) and
-                 emits the input bits of its windows (lo, hi]."""
+        """Mirror of tb_block<> in viterbi.cu: walks keep a shift register `path` (low M bits = state, bit b =
+        input of step tau_cur-(M-1)+b); phase A retires a path wherever it misses best[tau]; every path is walked
+        `ext` further steps and contributes (path << (lo-ts)) & bits[lo-ts, hi-ts)."""
         p0 = ts - D + 2
-        acc = {}
+        ext = max(D - 2 - (M - 1) - 1, 0)
+        dsh = 1 if (D - 2 - (M - 1) - 1) < 0 else 0
+        width = 64 if final else 32
+
+        def step(path, sl):
+            st = path & (S - 1)
+            path = ((path << 1) | int(ring_w[sl, st])) & ((1 << width) - 1)
+            return path, (R - 1 if sl == 0 else sl - 1)
+
+        def contribution(path, lo, hi):
+            v = ((path << (lo - ts)) & ((1 << width) - 1)) >> dsh
+            v &= ((1 << width) - 1) & ~((1 << (lo - ts)) - 1)
+            if not (final and hi == te):
+                v &= (1 << (hi - ts)) - 1
+            return v
+
+        acc = 0
         tasks = []
-
-        def wclamp(tau):
-            w = tau + D - 2 - (M - 1)
-            return te if (final and w > te) else w
-
         hi = te
         sl = slot_te
-        s = int(ring_b[sl])
+        path = int(ring_b[sl])
         for tau in range(te, ts, -1):
-            if tau < hi and s != int(ring_b[sl]):
-                tasks.append((tau, s, sl, tau, hi))          # retire: (tau_b, state at tau_b, slot, lo, hi)
+            b = int(ring_b[sl])
+            if tau < hi and (path & (S - 1)) != b:
+                tasks.append((tau, hi, path & 0xFFFFFFFF))
                 hi = tau
-                s = int(ring_b[sl])
-            q = tau - (M - 1)
-            if q >= 1 and wclamp(tau) <= hi:
-                acc[q - 1 - p0] = s & 1
-            s = ((s << 1) & (S - 1)) | int(ring_w[sl, s])
-            sl = R - 1 if sl == 0 else sl - 1
-        tasks.append((ts, s, sl, ts, hi))
+                path = b
+            path, sl = step(path, sl)
+        for _ in range(ext):
+            path, sl = step(path, sl)
+        acc |= contribution(path, ts, hi)
         if stats is not None:
             stats["tasks"] = stats.get("tasks", 0) + len(tasks)
-            stats.setdefault("blocks", []).append(len(tasks))
-        for (tb, s, sl, lo, hi) in tasks:
-            for tau in range(tb, tb - (D - 2 - (M - 1)), -1):
-                q = tau - (M - 1)
-                w = wclamp(tau)
-                if q >= 1 and lo < w <= hi:
-                    acc[q - 1 - p0] = s & 1
-                s = ((s << 1) & (S - 1)) | int(ring_w[sl, s])
-                sl = R - 1 if sl == 0 else sl - 1
-        cnt = (L - p0) if final else TBB
+        slot_ts = (slot_te - (te - ts)) % R
+        for (lo, thi, pth) in tasks:
+            sl = (slot_ts + (lo - ts)) % R
+            for _ in range(ext):
+                pth, sl = step(pth, sl)
+            acc |= contribution(pth, lo, thi)
+        cnt = (L - p0) if final else (te - ts)
         for i in range(cnt):
-            out[p0 + i] = acc[i]
+            out[p0 + i] = (acc >> i) & 1
 
     for tau in range(1, T + 1):
         if mode == "hard":
