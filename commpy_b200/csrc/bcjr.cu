@@ -25,6 +25,7 @@ const int32_t *cpb_trellis_next_dev(const cpbTrellis *t);
 const int32_t *cpb_trellis_out_dev(const cpbTrellis *t);
 void cpb_trellis_dims(const cpbTrellis *t, int *k, int *n, int *S);
 const int32_t *cpb_trellis_pred_dev(const cpbTrellis *t);
+void cpb_trellis_host_tables(const cpbTrellis *t, const int32_t **next, const int32_t **out);
 
 namespace bcjr {
 
@@ -139,6 +140,228 @@ __global__ void __launch_bounds__(128) map_kernel(const float *__restrict__ sys,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-resident MAP kernel: ONE THREAD per (frame, window), all S <= 8 state metrics in registers, the
+// trellis baked in at compile time (NEXT/OUT pack Trellis.next_state_table / output_table, 3 and 2 bits per
+// entry), so every table look-up is a register name.  Metrics live in the log2 domain: with a = ys*log2e/s^2,
+// b = yp*log2e/s^2 the branch metric of output (cs,cp) is +-a +-b (terms common to all branches of a step
+// cancel in every max* and in the LLR), max*(x,y) = max + lg2(1 + ex2(-|x-y|)) is two raw MUFU ops.
+// A frame longer than 1536 steps is cut into windows of 1024 steps; alpha starts 96 steps before its window and
+// beta 96 steps after it from uniform metrics (the true boundary values where the window touches the frame
+// ends).  SURVEY.md section 7-5 measured this warm-up against the reference's full-frame recursion: <= 3.4e-7
+// on the LLRs, i.e. inside fp32 round-off; the split depends only on N, never on the batch, so a frame decodes
+// identically whatever it is batched with.
+// ------------------------------------------------------------------------------------------------
+namespace tpf {
+
+constexpr float NEGM = -1.0e30f;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr int WIN = 1024, WARM = 96;
+
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float maxstar2(float x, float y)
+{
+    return fmaxf(x, y) + lg2(1.0f + ex2(-fabsf(x - y)));
+}
+
+template <int S_, unsigned long long NEXT_, unsigned int OUT_>
+struct CT {
+    static constexpr int S = S_;
+    __host__ __device__ static constexpr int ns(int s, int u) { return (int)((NEXT_ >> (3 * (2 * s + u))) & 7ull); }
+    __host__ __device__ static constexpr int out(int s, int u) { return (int)((OUT_ >> (2 * (2 * s + u))) & 3u); }
+    // idx-th edge (packed 2*s+u) entering state n, in (s asc, u asc) order
+    __host__ __device__ static constexpr int pred(int n, int idx)
+    {
+        int c = 0;
+        for (int e = 0; e < 2 * S_; ++e)
+            if (ns(e >> 1, e & 1) == n) { if (c == idx) return e; ++c; }
+        return -1;
+    }
+    __host__ __device__ static constexpr bool valid()
+    {
+        for (int n = 0; n < S_; ++n) { if (pred(n, 1) < 0 || pred(n, 2) >= 0) return false; }
+        return true;
+    }
+};
+
+struct Params {
+    const float *sys, *par, *La;
+    int64_t batch, bp;           // frames, frames padded to a multiple of 32
+    int N, nwin, win;            // frame length, windows per frame, steps per window
+    float c;                     // log2(e) / sigma^2
+    int mode;
+    float *beta;                 // [(tloc*S + s) * NT + thread]
+    int64_t NT;
+    float *L_out;
+    uint8_t *bits_out;
+};
+
+template <class T, int G>     // G = steps per vector access (4: float4 / uchar4, 1: scalar)
+__global__ void __launch_bounds__(128) map_tpf_kernel(const Params p)
+{
+    constexpr int S = T::S;
+    static_assert(T::valid(), "every state needs exactly two incoming edges");
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.NT) return;
+    const int w = (int)(g / p.bp);
+    const int64_t f = g - (int64_t)w * p.bp;
+    if (f >= p.batch) return;
+    const int N = p.N;
+    const int lo = w * p.win, hi = min(N, lo + p.win);       // this thread emits steps lo+1 .. hi
+    const float *fs = p.sys + f * N, *fp = p.par + f * N, *fl = p.La + f * N;
+    float *bcol = p.beta + g;
+
+    float A[S], B[S];
+    auto branch = [&](float ys, float yp, float (&gm)[4]) {
+        const float a = ys * p.c, b = yp * p.c;
+        gm[0] = -a - b; gm[1] = b - a; gm[2] = a - b; gm[3] = a + b;      // output symbol (cs,cp): MSB = systematic
+    };
+    auto load = [&](const float *q, int e0, float (&v)[G]) {            // elements e0 .. e0+G-1 (0-based)
+        if (G == 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(q + e0));
+            v[0] = t.x; v[1 % G] = t.y; v[2 % G] = t.z; v[3 % G] = t.w;
+        } else {
+            v[0] = __ldg(q + e0);
+        }
+    };
+
+    // ---- backward: beta_t for t = tb .. lo+1, stored for t <= hi
+    {
+        const int tb = min(N, hi + WARM);
+#pragma unroll
+        for (int s = 0; s < S; ++s) B[s] = 0.0f;                          // beta_N = 1 / uniform warm-up start
+        for (int e1 = tb; e1 > lo; e1 -= G) {                             // steps e1, e1-1, .., e1-G+1
+            float vs[G], vp[G], vl[G];
+            load(fs, e1 - G, vs); load(fp, e1 - G, vp); load(fl, e1 - G, vl);
+#pragma unroll
+            for (int i = G - 1; i >= 0; --i) {
+                const int t = e1 - (G - 1 - i);
+                if (t <= hi) {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) bcol[((int64_t)(t - lo - 1) * S + s) * p.NT] = B[s];
+                }
+                float gm[4];
+                branch(vs[i], vp[i], gm);
+                const float la = vl[i] * LOG2E;
+                float Bn[S];
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    Bn[s] = maxstar2(B[T::ns(s, 0)] + gm[T::out(s, 0)], B[T::ns(s, 1)] + gm[T::out(s, 1)] + la);
+                if ((t & 3) == 1) {                                       // renormalise every 4th step
+                    float m = Bn[0];
+#pragma unroll
+                    for (int s = 1; s < S; ++s) m = fmaxf(m, Bn[s]);
+#pragma unroll
+                    for (int s = 0; s < S; ++s) Bn[s] -= m;
+                }
+#pragma unroll
+                for (int s = 0; s < S; ++s) B[s] = Bn[s];
+            }
+        }
+    }
+    // ---- forward: alpha from ta, LLRs for t = lo+1 .. hi
+    {
+        const int ta = max(0, lo - WARM);
+#pragma unroll
+        for (int s = 0; s < S; ++s) A[s] = (ta == 0 && s != 0) ? NEGM : 0.0f;   // alpha_0 = delta(s,0) / uniform
+        for (int e0 = ta; e0 < hi; e0 += G) {                              // steps e0+1 .. e0+G
+            float vs[G], vp[G], vl[G];
+            load(fs, e0, vs); load(fp, e0, vp); load(fl, e0, vl);
+            float Lv[G];
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const int t = e0 + 1 + i;
+                float gm[4];
+                branch(vs[i], vp[i], gm);
+                const float la = vl[i] * LOG2E;
+                float tx[2 * S];
+#pragma unroll
+                for (int e = 0; e < 2 * S; ++e) tx[e] = A[e >> 1] + gm[T::out(e >> 1, e & 1)];
+                Lv[i] = 0.0f;
+                if (t > lo) {
+                    float x0[S], x1[S];
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        const float b0 = bcol[((int64_t)(t - lo - 1) * S + T::ns(s, 0)) * p.NT];
+                        const float b1 = bcol[((int64_t)(t - lo - 1) * S + T::ns(s, 1)) * p.NT];
+                        x0[s] = tx[2 * s] + b0;                            // APP terms exclude the prior (turbo.py:141-143)
+                        x1[s] = tx[2 * s + 1] + b1;
+                    }
+                    float m0 = x0[0], m1 = x1[0];
+#pragma unroll
+                    for (int s = 1; s < S; ++s) { m0 = fmaxf(m0, x0[s]); m1 = fmaxf(m1, x1[s]); }
+                    float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) { s0 += ex2(x0[s] - m0); s1 += ex2(x1[s] - m1); }
+                    Lv[i] = vl[i] + LN2 * ((m1 + lg2(s1)) - (m0 + lg2(s0)));   // turbo.py:145
+                }
+                float An[S];
+#pragma unroll
+                for (int n = 0; n < S; ++n) {
+                    const int ea = T::pred(n, 0), eb = T::pred(n, 1);
+                    An[n] = maxstar2(tx[ea] + ((ea & 1) ? la : 0.0f), tx[eb] + ((eb & 1) ? la : 0.0f));
+                }
+                if ((t & 3) == 0) {
+                    float m = An[0];
+#pragma unroll
+                    for (int s = 1; s < S; ++s) m = fmaxf(m, An[s]);
+#pragma unroll
+                    for (int s = 0; s < S; ++s) An[s] = fmaxf(An[s] - m, NEGM);
+                }
+#pragma unroll
+                for (int s = 0; s < S; ++s) A[s] = An[s];
+            }
+            if (e0 >= lo) {
+                if (G == 4) {
+                    *reinterpret_cast<float4 *>(p.L_out + f * N + e0) = make_float4(Lv[0], Lv[1 % G], Lv[2 % G], Lv[3 % G]);
+                    if (p.bits_out) {
+                        uchar4 b;
+                        b.x = (p.mode == 1 && Lv[0] > 0.0f); b.y = (p.mode == 1 && Lv[1 % G] > 0.0f);
+                        b.z = (p.mode == 1 && Lv[2 % G] > 0.0f); b.w = (p.mode == 1 && Lv[3 % G] > 0.0f);
+                        *reinterpret_cast<uchar4 *>(p.bits_out + f * N + e0) = b;
+                    }
+                } else {
+                    p.L_out[f * N + e0] = Lv[0];
+                    if (p.bits_out) p.bits_out[f * N + e0] = (uint8_t)((p.mode == 1 && Lv[0] > 0.0f) ? 1 : 0);   // :148-152
+                }
+            }
+        }
+    }
+}
+
+// compile-time trellises this kernel is instantiated for (packed from commpy_b200's Trellis tables)
+using RscK4 = CT<8, 0xedfc96369120ull, 0xc99cc99cu>;         // Trellis([3], [[1, 0o15]], [[0o13]], 'rsc')  (config C3)
+using RscK4Legacy = CT<8, 0xedf5b2a4d120ull, 0xcc9999ccu>;   // Trellis([3], [[1, 0o15]], 0o13, 'rsc')
+using RscK3Legacy = CT<4, 0x2d9090ull, 0x99ccu>;             // Trellis([2], [[1, 7]], 5, 'rsc')     (test_convcode.py:37)
+using FfK3 = CT<4, 0x659410ull, 0x693cu>;                    // Trellis([2], [[5, 7]])
+using RscK3 = CT<4, 0x64b090ull, 0x9c9cu>;                   // Trellis([2], [[1, 5]], [[7]], 'rsc')
+
+template <class T>
+static bool matches(const int32_t *next, const int32_t *out, int S)
+{
+    if (S != T::S) return false;
+    for (int s = 0; s < S; ++s)
+        for (int u = 0; u < 2; ++u)
+            if (next[s * 2 + u] != T::ns(s, u) || out[s * 2 + u] != T::out(s, u)) return false;
+    return true;
+}
+
+static int nwindows(int N) { return (N > WIN + WIN / 2) ? (int)ceil_div(N, WIN) : 1; }
+
+template <class T>
+static int launch(const Params &p, bool vec, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)ceil_div(p.NT, 128);
+    if (vec) map_tpf_kernel<T, 4><<<grid, 128, 0, st>>>(p);
+    else map_tpf_kernel<T, 1><<<grid, 128, 0, st>>>(p);
+    CPB_LAUNCH_CHECK();
+    return CPB_OK;
+}
+
+}  // namespace tpf
+
 // out[f][i] = a[f][perm[i]] - (b ? b[f][perm[i]] : 0)        interleave (interleavers.py:13-29) of an extrinsic
 __global__ void __launch_bounds__(256) gather_sub_kernel(const float *__restrict__ a, const float *__restrict__ b,
                                                          const int32_t *__restrict__ perm, int64_t batch, int N,
@@ -178,9 +401,37 @@ __global__ void __launch_bounds__(256) scatter_bits_kernel(const uint8_t *__rest
     }
 }
 
+// floats of beta scratch one chunk of `frames` frames needs (whichever kernel runs)
+static size_t beta_floats(int64_t frames, int N, int S)
+{
+    const int nwin = tpf::nwindows(N);
+    const int win = (nwin == 1) ? N : tpf::WIN;
+    const int64_t bp = ceil_div(frames, 32) * 32;
+    const size_t a = (size_t)frames * (N + 1) * S;
+    const size_t b = (size_t)nwin * bp * win * S;
+    return std::max(a, b);
+}
+
 static int launch_map(const cpbTrellis *t, int S, const float *sys, const float *par, const float *La, int64_t batch,
                       int N, float noise_var, int mode, float *beta, float *L_out, uint8_t *bits, cudaStream_t st)
 {
+    const int32_t *hn = nullptr, *ho = nullptr;
+    cpb_trellis_host_tables(t, &hn, &ho);
+    {
+        tpf::Params p{};
+        p.sys = sys; p.par = par; p.La = La; p.batch = batch; p.bp = ceil_div(batch, 32) * 32;
+        p.N = N; p.nwin = tpf::nwindows(N); p.win = (p.nwin == 1) ? N : tpf::WIN;
+        p.c = tpf::LOG2E / noise_var; p.mode = mode; p.beta = beta; p.NT = (int64_t)p.nwin * p.bp;
+        p.L_out = L_out; p.bits_out = bits;
+        const bool vec = (N % 4 == 0) && ((((uintptr_t)sys | (uintptr_t)par | (uintptr_t)La | (uintptr_t)L_out) & 15) == 0) &&
+                         (bits == nullptr || (((uintptr_t)bits) & 3) == 0);
+        if (tpf::matches<tpf::RscK4>(hn, ho, S)) return tpf::launch<tpf::RscK4>(p, vec, st);
+        if (tpf::matches<tpf::RscK4Legacy>(hn, ho, S)) return tpf::launch<tpf::RscK4Legacy>(p, vec, st);
+        if (tpf::matches<tpf::RscK3Legacy>(hn, ho, S)) return tpf::launch<tpf::RscK3Legacy>(p, vec, st);
+        if (tpf::matches<tpf::FfK3>(hn, ho, S)) return tpf::launch<tpf::FfK3>(p, vec, st);
+        if (tpf::matches<tpf::RscK3>(hn, ho, S)) return tpf::launch<tpf::RscK3>(p, vec, st);
+    }
+    // any other rate-1/2 trellis with 2..32 states: table-driven lane-per-state kernel
     const int32_t *nx = cpb_trellis_next_dev(t), *ot = cpb_trellis_out_dev(t), *pd = cpb_trellis_pred_dev(t);
     const float inv2s2 = 1.0f / (2.0f * noise_var);
     const int fpw = 32 / S;
@@ -208,7 +459,7 @@ static int check_trellis(const cpbTrellis *t, int *S)
 
 static int64_t chunk_frames(int64_t batch, int N, int S)
 {
-    const double per = (double)(N + 1) * S * 4.0 + 5.0 * N * 4.0 + N;
+    const double per = (double)(N + tpf::WIN + 1) * S * 4.0 + 5.0 * N * 4.0 + N;
     int64_t c = (int64_t)(6.0e9 / per);
     if (c < 1) c = 1;
     return std::min<int64_t>(c, batch);
@@ -231,7 +482,7 @@ int cpb_map_decode(const cpbTrellis *t, const float *sys_dev, const float *par_d
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t Fc = bcjr::chunk_frames(batch, (int)N, S);
     Scratch ws;
-    rc = ws.acquire(nullptr, 0, (size_t)Fc * (N + 1) * S * sizeof(float), st);
+    rc = ws.acquire(nullptr, 0, bcjr::beta_floats(Fc, (int)N, S) * sizeof(float), st);
     if (rc) return rc;
     for (int64_t f0 = 0; f0 < batch && rc == CPB_OK; f0 += Fc) {
         const int64_t nb = std::min<int64_t>(Fc, batch - f0);
@@ -257,7 +508,7 @@ int cpb_turbo_decode(const cpbTrellis *t, const float *sys_dev, const float *par
     cudaStream_t st = (cudaStream_t)stream;
     const DeviceProps &dp = device_props();
     const int64_t Fc = bcjr::chunk_frames(batch, (int)N, S);
-    const size_t nbeta = (size_t)Fc * (N + 1) * S, nvec = (size_t)Fc * N;
+    const size_t nbeta = bcjr::beta_floats(Fc, (int)N, S), nvec = (size_t)Fc * N;
     Scratch ws;
     rc = ws.acquire(nullptr, 0, (nbeta + 5 * nvec) * sizeof(float) + nvec + 256, st);
     if (rc) return rc;

@@ -757,6 +757,11 @@ const int32_t *cpb_trellis_next_dev(const cpbTrellis *t) { return t->next_dev; }
 const int32_t *cpb_trellis_out_dev(const cpbTrellis *t) { return t->out_dev; }
 const int32_t *cpb_trellis_pred_dev(const cpbTrellis *t) { return t->pred_dev; }
 void cpb_trellis_dims(const cpbTrellis *t, int *k, int *n, int *S) { *k = t->k; *n = t->n; *S = t->S; }
+void cpb_trellis_host_tables(const cpbTrellis *t, const int32_t **next, const int32_t **out)
+{
+    *next = t->next_state.data();
+    *out = t->output.data();
+}
 
 static int resolve_depth(const cpbTrellis *t, int64_t L, int tb_depth)
 {

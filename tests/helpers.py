@@ -71,3 +71,41 @@ def channel_frames(trellis, rs, batch, nbits, mode, termination="cont", flip=0.0
         y = (2 * coded - 1) + np.sqrt(sigma2) * rs.randn(*coded.shape)
         x = 2 * y / sigma2 if mode == "soft" else y
     return msgs, x
+
+
+def dvbs2_like_H(seed=3, n=64800, m=32400, n8=12960, n3=19440):
+    """DVB-S2-SHAPED surrogate parity-check matrix (the reference ships no DVB-S2 design and there is no network,
+    SURVEY.md section 7-3): same size (32400 x 64800), same degree profile as the rate-1/2 normal frame
+    (12,960 information columns of degree 8, 19,440 of degree 3, dual-diagonal staircase parity part, every
+    check of degree 7 except the first: 226,799 edges), information edges placed pseudo-randomly from `seed`.
+    It is NOT the ETSI EN 302 307 address table.  Returns a scipy CSR int8 matrix."""
+    import scipy.sparse as sp
+    rs = np.random.RandomState(seed)
+    k = n - m
+    assert n8 + n3 == k
+    deg = np.concatenate([np.full(n8, 8), np.full(n3, 3)])
+    slots = np.repeat(np.arange(m), (deg.sum() + m - 1) // m)[:deg.sum()]       # 5 information edges per check
+    for _ in range(200):
+        rs.shuffle(slots)
+        cols = np.repeat(np.arange(k), deg)
+        key = cols.astype(np.int64) * m + slots
+        order = np.argsort(key, kind="stable")
+        dup = np.zeros(len(key), bool)
+        dup[order[1:]] = key[order][1:] == key[order][:-1]
+        if not dup.any():
+            break
+        # repair duplicates by swapping the offending slots with random other positions
+        bad = np.nonzero(dup)[0]
+        other = rs.randint(0, len(slots), len(bad))
+        slots[bad], slots[other] = slots[other].copy(), slots[bad].copy()
+        key = cols.astype(np.int64) * m + slots
+        if len(np.unique(key)) == len(key):
+            break
+    rows = [slots, np.arange(m), np.arange(1, m)]
+    colsl = [np.repeat(np.arange(k), deg), k + np.arange(m), k + np.arange(m - 1)]
+    r = np.concatenate(rows)
+    c = np.concatenate(colsl)
+    H = sp.csr_matrix((np.ones(len(r), np.int8), (r, c)), shape=(m, n))
+    H.data[:] = 1
+    H.sort_indices()
+    return H

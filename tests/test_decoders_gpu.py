@@ -227,3 +227,61 @@ def test_count_errors():
     _lib.check(rc, "count")
     got = cnt.cpu().numpy()
     assert got[0] == int(flips.sum()) and got[1] == int(flips.any(axis=1).sum())
+
+
+def test_ldpc_dvbs2_size_surrogate_exact_fp64_and_converged_fp32():
+    """C4 shape: (64800, 32400), 226,799 edges (DVB-S2-SHAPED surrogate, helpers.dvbs2_like_H)."""
+    H = helpers.dvbs2_like_H()
+    params = {"n_vnodes": 64800, "n_cnodes": 32400, "parity_check_matrix": H.tocsc()}
+    rs = np.random.RandomState(26)
+    frames = []
+    for eb in (1.0, 2.6, 2.6, 3.0):          # one frame that does not converge, three that do
+        sigma = 1.0 / np.sqrt(2 * 0.5 * 10 ** (eb / 10))
+        frames.append(2.0 * (1.0 + sigma * rs.randn(64800)) / sigma ** 2)
+    llr = np.stack(frames)
+    want_dec, want_out, want_it = oracle.ldpc_bp_decode(llr.reshape(-1).copy(), params, "MSA", 12, return_iters=True,
+                                                        threads=4)
+    want_dec, want_out = want_dec.T, want_out.T
+    dec, out, it = ldpc_bp_decode_batch(llr.copy(), params, 12, "fp64", return_iters=True)
+    assert np.array_equal(it.cpu().numpy(), want_it)
+    assert np.array_equal(dec.cpu().numpy(), want_dec)
+    assert np.array_equal(out.cpu().numpy(), want_out)
+    dec32, out32, it32 = ldpc_bp_decode_batch(llr.astype(np.float32), params, 12, "fp32", return_iters=True)
+    conv = want_it < 12
+    assert conv.sum() >= 2
+    assert np.array_equal(dec32.cpu().numpy()[conv], want_dec[conv])
+    assert np.array_equal(it32.cpu().numpy()[conv], want_it[conv])
+
+
+def test_map_decode_generic_trellis_fallback_kernel():
+    """A trellis that is not one of the compile-time instances goes through the table-driven lane-per-state kernel."""
+    from commpy_b200.channelcoding import Trellis
+    rs = np.random.RandomState(27)
+    for tr in (Trellis(np.array([3]), np.array([[0o15, 0o17]])), Trellis(np.array([4]), np.array([[0o23, 0o35]]))):
+        N = 400
+        msg = rs.randint(0, 2, N)
+        coded = conv_encode(msg, tr, "cont")
+        s2 = 0.7
+        ys = 2.0 * coded[0::2] - 1 + np.sqrt(s2) * rs.randn(N)
+        yp = 2.0 * coded[1::2] - 1 + np.sqrt(s2) * rs.randn(N)
+        La = rs.randn(N)
+        L, bits = map_decode(ys, yp, tr, s2, La, "decode")
+        Lo, bo = oracle.map_decode(ys, yp, tr, s2, La, "decode")
+        assert (np.abs(L - Lo) <= MAP_ATOL + MAP_RTOL * np.abs(Lo)).all(), float(np.abs(L - Lo).max())
+        safe = np.abs(Lo) > 1e-3
+        assert np.array_equal(bits[safe], bo[safe])
+
+
+def test_map_decode_unaligned_length_scalar_path():
+    tr = helpers.rsc_k4()
+    rs = np.random.RandomState(28)
+    for N in (37, 1537, 2049):                   # not multiples of 4; 1537 and 2049 are split into windows
+        msg = rs.randint(0, 2, N)
+        coded = conv_encode(msg, tr, "cont")
+        s2 = 0.8
+        ys = 2.0 * coded[0::2] - 1 + np.sqrt(s2) * rs.randn(N)
+        yp = 2.0 * coded[1::2] - 1 + np.sqrt(s2) * rs.randn(N)
+        La = 0.5 * rs.randn(N)
+        L, _ = map_decode(ys, yp, tr, s2, La, "decode")
+        Lo, _ = oracle.map_decode(ys, yp, tr, s2, La, "decode")
+        assert (np.abs(L - Lo) <= MAP_ATOL + MAP_RTOL * np.abs(Lo)).all(), (N, float(np.abs(L - Lo).max()))
