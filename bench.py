@@ -407,7 +407,7 @@ def run_extras(torch):
         import helpers
         from commpy_b200.channelcoding import RandInterlv, turbo_decode_batch
         tr = helpers.rsc_k4()
-        N, batch = 6144, 2048
+        N, batch = 6144, 8192          # config C3's batch
         il = RandInterlv(N, 1)
         s2 = 1.0 / (2 * (1 / 3) * 10 ** (1.0 / 10))
         ys, y1, y2 = ((-1 + s2 ** 0.5 * torch.randn(batch, N, device="cuda")).float() for _ in range(3))

@@ -61,10 +61,40 @@ static double orc_branch_metric(int mode, const double *r, int code, int n)
  * decoded: L int64 (L = int(len*k/n)).  tb_depth <= 0 selects the default
  * min(5*total_memory, L) (convcode.py:701-702).  mode 0 hard, 1 soft, 2 unquantized.
  */
+/* scratch of one decode; the batch entry point allocates it once and reuses it for every frame of its chunk */
+typedef struct {
+    int32_t *pred_state, *pred_input, *pred_cnt, *paths, *dsym;
+    double *pm, *cb, *rpad;
+    int64_t *dbits;
+} orc_vit_ws;
+
+static void orc_vit_ws_free(orc_vit_ws *w)
+{
+    free(w->pred_state); free(w->pred_input); free(w->pred_cnt); free(w->pm); free(w->paths);
+    free(w->dsym); free(w->dbits); free(w->cb); free(w->rpad);
+}
+
+static int orc_viterbi_core(const double *coded, int64_t len,
+                            const int32_t *next_state, const int32_t *output,
+                            int k, int n, int total_memory, int S,
+                            int tb_depth, int mode, int64_t *decoded, orc_vit_ws *ws);
+
 int orc_viterbi_decode(const double *coded, int64_t len,
                        const int32_t *next_state, const int32_t *output,
                        int k, int n, int total_memory, int S,
                        int tb_depth, int mode, int64_t *decoded)
+{
+    orc_vit_ws ws;
+    memset(&ws, 0, sizeof(ws));
+    int rc = orc_viterbi_core(coded, len, next_state, output, k, n, total_memory, S, tb_depth, mode, decoded, &ws);
+    orc_vit_ws_free(&ws);
+    return rc;
+}
+
+static int orc_viterbi_core(const double *coded, int64_t len,
+                            const int32_t *next_state, const int32_t *output,
+                            int k, int n, int total_memory, int S,
+                            int tb_depth, int mode, int64_t *decoded, orc_vit_ws *ws)
 {
     if (k <= 0 || n <= 0 || S <= 0 || mode < 0 || mode > 2) return ORC_EBADARG;
     const int I = 1 << k;
@@ -78,18 +108,28 @@ int orc_viterbi_decode(const double *coded, int64_t len,
     const int D = tb_depth;
 
     /* _where_c (convcode.py:561-572): predecessors in (prev_state asc, input asc) order */
-    int32_t *pred_state = (int32_t *)malloc(sizeof(int32_t) * S * I);
-    int32_t *pred_input = (int32_t *)malloc(sizeof(int32_t) * S * I);
-    int32_t *pred_cnt = (int32_t *)calloc(S, sizeof(int32_t));
-    double *pm = (double *)malloc(sizeof(double) * S * 2);
-    int32_t *paths = (int32_t *)calloc((size_t)S * D, sizeof(int32_t));
-    int32_t *dsym = (int32_t *)calloc((size_t)S * D, sizeof(int32_t));
     const int64_t nbuf = ((L + D + k - 1) / k) * k + k;
-    int64_t *dbits = (int64_t *)calloc((size_t)nbuf, sizeof(int64_t));
-    double *cb = (double *)malloc(sizeof(double) * (len > 0 ? len : 1));
-    double *rpad = (double *)malloc(sizeof(double) * n);
+    if (!ws->pm) {        /* first frame of this workspace: sizes are identical for every frame of a batch */
+        ws->pred_state = (int32_t *)malloc(sizeof(int32_t) * S * I);
+        ws->pred_input = (int32_t *)malloc(sizeof(int32_t) * S * I);
+        ws->pred_cnt = (int32_t *)malloc(sizeof(int32_t) * S);
+        ws->pm = (double *)malloc(sizeof(double) * S * 2);
+        ws->paths = (int32_t *)malloc(sizeof(int32_t) * (size_t)S * D);
+        ws->dsym = (int32_t *)malloc(sizeof(int32_t) * (size_t)S * D);
+        ws->dbits = (int64_t *)malloc(sizeof(int64_t) * (size_t)nbuf);
+        ws->cb = (double *)malloc(sizeof(double) * (len > 0 ? len : 1));
+        ws->rpad = (double *)malloc(sizeof(double) * n);
+    }
+    int32_t *pred_state = ws->pred_state, *pred_input = ws->pred_input, *pred_cnt = ws->pred_cnt;
+    double *pm = ws->pm, *cb = ws->cb, *rpad = ws->rpad;
+    int32_t *paths = ws->paths, *dsym = ws->dsym;
+    int64_t *dbits = ws->dbits;
     if (!pred_state || !pred_input || !pred_cnt || !pm || !paths || !dsym || !dbits || !cb || !rpad)
         return ORC_EALLOC;
+    memset(pred_cnt, 0, sizeof(int32_t) * S);
+    memset(paths, 0, sizeof(int32_t) * (size_t)S * D);       /* np.empty / np.zeros of convcode.py:707-711 */
+    memset(dsym, 0, sizeof(int32_t) * (size_t)S * D);
+    memset(dbits, 0, sizeof(int64_t) * (size_t)nbuf);
     int rc = ORC_OK;
     for (int p = 0; p < S; ++p)
         for (int u = 0; u < I; ++u) {
@@ -151,8 +191,6 @@ int orc_viterbi_decode(const double *coded, int64_t len,
     }
     for (int64_t i = 0; i < L; ++i) decoded[i] = dbits[i];                          /* :749 */
 done:
-    free(pred_state); free(pred_input); free(pred_cnt); free(pm); free(paths);
-    free(dsym); free(dbits); free(cb); free(rpad);
     return rc;
 }
 
@@ -169,11 +207,14 @@ int orc_viterbi_decode_batch(const double *coded, int64_t batch, int64_t len,
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #pragma omp parallel for schedule(dynamic, 1)
 #endif
+    orc_vit_ws ws;
+    memset(&ws, 0, sizeof(ws));
     for (int64_t b = 0; b < batch; ++b) {
-        int r = orc_viterbi_decode(coded + b * len, len, next_state, output, k, n, total_memory, S,
-                                   tb_depth, mode, decoded + b * L);
+        int r = orc_viterbi_core(coded + b * len, len, next_state, output, k, n, total_memory, S,
+                                 tb_depth, mode, decoded + b * L, &ws);
         if (r != ORC_OK) rc = r;
     }
+    orc_vit_ws_free(&ws);
     return rc;
 }
 
