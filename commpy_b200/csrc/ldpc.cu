@@ -109,13 +109,16 @@ __global__ void finish_iters_kernel(const State st, int64_t batch, int n_iters, 
     if (f < batch) iters_out[f] = st.done[f] ? st.iters[f] : n_iters;
 }
 
-template <typename T>
+// DEGMAX > 0: rows of degree <= DEGMAX keep their variable-to-check messages in registers between the two passes
+// (one read of R and post per edge); DEGMAX == 0: any degree, messages are recomputed in the second pass.
+template <typename T, int DEGMAX>
 __global__ void __launch_bounds__(256) cn_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
                                                  int m, int64_t F, int iter, const T *__restrict__ post,
                                                  T *__restrict__ R, const State st)
 {
     using VT = typename VecOf<T>::type;
     constexpr int V = VecOf<T>::V;
+    constexpr int QN = (DEGMAX > 0) ? DEGMAX : 1;
     const int64_t G = F / V;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (int64_t)m * G) return;
@@ -131,36 +134,82 @@ __global__ void __launch_bounds__(256) cn_kernel(const int32_t *__restrict__ row
     int arg[V], neg[V], par[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) { min1[v] = (T)INFINITY; min2[v] = (T)INFINITY; arg[v] = -1; neg[v] = 0; par[v] = 0; }
-    for (int e = e0; e < e1; ++e) {
-        const int c = __ldg(&col_idx[e]);
-        const VT p = *reinterpret_cast<const VT *>(post + (int64_t)c * F + f);
-        const VT r = *reinterpret_cast<const VT *>(R + (int64_t)e * F + f);
+    VT q[QN];
+    if (DEGMAX > 0) {
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-            par[v] ^= signbit(p.v[v]) ? 1 : 0;
-            const T q = p.v[v] - r.v[v];                  // Q_ij = (tot_j + llr_j) - R_ij, ldpc.py:244-245
-            const T a = fabs(q);
-            neg[v] += (q < (T)0) ? 1 : 0;
-            if (a < min1[v]) { min2[v] = min1[v]; min1[v] = a; arg[v] = e; }
-            else if (a < min2[v]) min2[v] = a;
+        for (int k = 0; k < QN; ++k) {
+            const int e = e0 + k;
+            if (e < e1) {
+                const int c = __ldg(&col_idx[e]);
+                const VT p = *reinterpret_cast<const VT *>(post + (int64_t)c * F + f);
+                const VT r = *reinterpret_cast<const VT *>(R + (int64_t)e * F + f);
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    par[v] ^= signbit(p.v[v]) ? 1 : 0;
+                    const T x = p.v[v] - r.v[v];              // Q_ij = (tot_j + llr_j) - R_ij, ldpc.py:244-245
+                    q[k].v[v] = x;
+                    const T a = fabs(x);
+                    neg[v] += (x < (T)0) ? 1 : 0;
+                    if (a < min1[v]) { min2[v] = min1[v]; min1[v] = a; arg[v] = k; }
+                    else if (a < min2[v]) min2[v] = a;
+                }
+            }
+        }
+    } else {
+        for (int e = e0; e < e1; ++e) {
+            const int c = __ldg(&col_idx[e]);
+            const VT p = *reinterpret_cast<const VT *>(post + (int64_t)c * F + f);
+            const VT r = *reinterpret_cast<const VT *>(R + (int64_t)e * F + f);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                par[v] ^= signbit(p.v[v]) ? 1 : 0;
+                const T x = p.v[v] - r.v[v];
+                const T a = fabs(x);
+                neg[v] += (x < (T)0) ? 1 : 0;
+                if (a < min1[v]) { min2[v] = min1[v]; min1[v] = a; arg[v] = e - e0; }
+                else if (a < min2[v]) min2[v] = a;
+            }
         }
     }
 #pragma unroll
     for (int v = 0; v < V; ++v)
         if (act[v] && par[v]) st.unsat_iter[f + v] = iter + 1;        // benign race: every writer stores the same value
-    for (int e = e0; e < e1; ++e) {
-        const int c = __ldg(&col_idx[e]);
-        const VT p = *reinterpret_cast<const VT *>(post + (int64_t)c * F + f);
-        VT r = *reinterpret_cast<const VT *>(R + (int64_t)e * F + f);
+    if (DEGMAX > 0) {
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-            const T q = p.v[v] - r.v[v];
-            const T mag = (e == arg[v]) ? min2[v] : min1[v];          // min over the OTHER edges (:238)
-            const int ng = neg[v] - ((q < (T)0) ? 1 : 0);
-            const T val = (ng & 1) ? -mag : mag;                      // prod of sign(others); a zero among them gives mag = 0
-            if (act[v]) r.v[v] = val;
+        for (int k = 0; k < QN; ++k) {
+            const int e = e0 + k;
+            if (e < e1) {
+                VT r;
+                bool all = true;
+#pragma unroll
+                for (int v = 0; v < V; ++v) all &= act[v];
+                if (!all) r = *reinterpret_cast<const VT *>(R + (int64_t)e * F + f);     // keep finished frames' messages
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const T x = q[k].v[v];
+                    const T mag = (k == arg[v]) ? min2[v] : min1[v];          // min over the OTHER edges (:238)
+                    const int ng = neg[v] - ((x < (T)0) ? 1 : 0);
+                    const T val = (ng & 1) ? -mag : mag;                      // prod of sign(others)
+                    if (act[v]) r.v[v] = val;
+                }
+                *reinterpret_cast<VT *>(R + (int64_t)e * F + f) = r;
+            }
         }
-        *reinterpret_cast<VT *>(R + (int64_t)e * F + f) = r;
+    } else {
+        for (int e = e0; e < e1; ++e) {
+            const int c = __ldg(&col_idx[e]);
+            const VT p = *reinterpret_cast<const VT *>(post + (int64_t)c * F + f);
+            VT r = *reinterpret_cast<const VT *>(R + (int64_t)e * F + f);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const T x = p.v[v] - r.v[v];
+                const T mag = ((e - e0) == arg[v]) ? min2[v] : min1[v];
+                const int ng = neg[v] - ((x < (T)0) ? 1 : 0);
+                const T val = (ng & 1) ? -mag : mag;
+                if (act[v]) r.v[v] = val;
+            }
+            *reinterpret_cast<VT *>(R + (int64_t)e * F + f) = r;
+        }
     }
 }
 
@@ -259,7 +308,8 @@ static int run(const cpbLdpc *h, T *llr, int64_t batch, int n_iters, uint8_t *de
         const unsigned cn_blocks = (unsigned)ceil_div((int64_t)h->m * G, 256);
         const unsigned vn_blocks = (unsigned)ceil_div((int64_t)h->n * G, 256);
         for (int it = 0; it < n_iters; ++it) {
-            cn_kernel<T><<<cn_blocks, 256, 0, st>>>(h->row_ptr, h->col_idx, h->m, F, it, post, R, s);
+            if (h->max_row_deg <= 8) cn_kernel<T, 8><<<cn_blocks, 256, 0, st>>>(h->row_ptr, h->col_idx, h->m, F, it, post, R, s);
+            else cn_kernel<T, 0><<<cn_blocks, 256, 0, st>>>(h->row_ptr, h->col_idx, h->m, F, it, post, R, s);
             vn_kernel<T><<<vn_blocks, 256, 0, st>>>(h->col_ptr, h->col_edge, h->n, F, it, llrT, R, post, s);
         }
         store_kernel<T><<<tgrid, 256, 0, st>>>(post, nb, h->n, F, dec + f0 * h->n, out_llr ? out_llr + f0 * h->n : nullptr);
