@@ -227,14 +227,18 @@ __global__ void __launch_bounds__(128) map_tpf_kernel(const Params p)
         }
     };
 
-    // ---- backward: beta_t for t = tb .. lo+1, stored for t <= hi
+    // ---- backward: beta_t for t = tb .. lo+1, stored for t <= hi (inputs prefetched one group ahead)
     {
         const int tb = min(N, hi + WARM);
 #pragma unroll
         for (int s = 0; s < S; ++s) B[s] = 0.0f;                          // beta_N = 1 / uniform warm-up start
+        float ns_[G], np_[G], nl_[G];
+        load(fs, tb - G, ns_); load(fp, tb - G, np_); load(fl, tb - G, nl_);
         for (int e1 = tb; e1 > lo; e1 -= G) {                             // steps e1, e1-1, .., e1-G+1
             float vs[G], vp[G], vl[G];
-            load(fs, e1 - G, vs); load(fp, e1 - G, vp); load(fl, e1 - G, vl);
+#pragma unroll
+            for (int i = 0; i < G; ++i) { vs[i] = ns_[i]; vp[i] = np_[i]; vl[i] = nl_[i]; }
+            if (e1 - G > lo) { load(fs, e1 - 2 * G, ns_); load(fp, e1 - 2 * G, np_); load(fl, e1 - 2 * G, nl_); }
 #pragma unroll
             for (int i = G - 1; i >= 0; --i) {
                 const int t = e1 - (G - 1 - i);
@@ -261,18 +265,36 @@ __global__ void __launch_bounds__(128) map_tpf_kernel(const Params p)
             }
         }
     }
-    // ---- forward: alpha from ta, LLRs for t = lo+1 .. hi
+    // ---- forward: alpha from ta, LLRs for t = lo+1 .. hi (inputs one group ahead, beta one step ahead)
     {
         const int ta = max(0, lo - WARM);
 #pragma unroll
         for (int s = 0; s < S; ++s) A[s] = (ta == 0 && s != 0) ? NEGM : 0.0f;   // alpha_0 = delta(s,0) / uniform
+        auto load_beta = [&](int t, float (&b)[S]) {
+            if (t > lo && t <= hi) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) b[s] = bcol[((int64_t)(t - lo - 1) * S + s) * p.NT];
+            }
+        };
+        float bnext[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) bnext[s] = 0.0f;
+        load_beta(ta + 1, bnext);
+        float ns_[G], np_[G], nl_[G];
+        load(fs, ta, ns_); load(fp, ta, np_); load(fl, ta, nl_);
         for (int e0 = ta; e0 < hi; e0 += G) {                              // steps e0+1 .. e0+G
             float vs[G], vp[G], vl[G];
-            load(fs, e0, vs); load(fp, e0, vp); load(fl, e0, vl);
+#pragma unroll
+            for (int i = 0; i < G; ++i) { vs[i] = ns_[i]; vp[i] = np_[i]; vl[i] = nl_[i]; }
+            if (e0 + G < hi) { load(fs, e0 + G, ns_); load(fp, e0 + G, np_); load(fl, e0 + G, nl_); }
             float Lv[G];
 #pragma unroll
             for (int i = 0; i < G; ++i) {
                 const int t = e0 + 1 + i;
+                float bt[S];
+#pragma unroll
+                for (int s = 0; s < S; ++s) bt[s] = bnext[s];
+                load_beta(t + 1, bnext);
                 float gm[4];
                 branch(vs[i], vp[i], gm);
                 const float la = vl[i] * LOG2E;
@@ -284,10 +306,8 @@ __global__ void __launch_bounds__(128) map_tpf_kernel(const Params p)
                     float x0[S], x1[S];
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
-                        const float b0 = bcol[((int64_t)(t - lo - 1) * S + T::ns(s, 0)) * p.NT];
-                        const float b1 = bcol[((int64_t)(t - lo - 1) * S + T::ns(s, 1)) * p.NT];
-                        x0[s] = tx[2 * s] + b0;                            // APP terms exclude the prior (turbo.py:141-143)
-                        x1[s] = tx[2 * s + 1] + b1;
+                        x0[s] = tx[2 * s] + bt[T::ns(s, 0)];               // APP terms exclude the prior (turbo.py:141-143)
+                        x1[s] = tx[2 * s + 1] + bt[T::ns(s, 1)];
                     }
                     float m0 = x0[0], m1 = x1[0];
 #pragma unroll

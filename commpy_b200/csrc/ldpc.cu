@@ -135,18 +135,26 @@ __global__ void __launch_bounds__(256) cn_kernel(const int32_t *__restrict__ row
 #pragma unroll
     for (int v = 0; v < V; ++v) { min1[v] = (T)INFINITY; min2[v] = (T)INFINITY; arg[v] = -1; neg[v] = 0; par[v] = 0; }
     VT q[QN];
+    const int deg = e1 - e0;
     if (DEGMAX > 0) {
+        // issue every load of the row before the first use (edges past the row's degree re-read its last edge, so
+        // no load is predicated and the memory system sees 2*DEGMAX independent 16-byte requests per thread)
+        int cix[QN];
+#pragma unroll
+        for (int k = 0; k < QN; ++k) cix[k] = __ldg(&col_idx[min(e0 + k, e1 - 1)]);
+        VT pv[QN];
 #pragma unroll
         for (int k = 0; k < QN; ++k) {
-            const int e = e0 + k;
-            if (e < e1) {
-                const int c = __ldg(&col_idx[e]);
-                const VT p = *reinterpret_cast<const VT *>(post + (int64_t)c * F + f);
-                const VT r = *reinterpret_cast<const VT *>(R + (int64_t)e * F + f);
+            pv[k] = *reinterpret_cast<const VT *>(post + (int64_t)cix[k] * F + f);
+            q[k] = *reinterpret_cast<const VT *>(R + (int64_t)min(e0 + k, e1 - 1) * F + f);
+        }
+#pragma unroll
+        for (int k = 0; k < QN; ++k) {
+            if (k < deg) {
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
-                    par[v] ^= signbit(p.v[v]) ? 1 : 0;
-                    const T x = p.v[v] - r.v[v];              // Q_ij = (tot_j + llr_j) - R_ij, ldpc.py:244-245
+                    par[v] ^= signbit(pv[k].v[v]) ? 1 : 0;
+                    const T x = pv[k].v[v] - q[k].v[v];       // Q_ij = (tot_j + llr_j) - R_ij, ldpc.py:244-245
                     q[k].v[v] = x;
                     const T a = fabs(x);
                     neg[v] += (x < (T)0) ? 1 : 0;
