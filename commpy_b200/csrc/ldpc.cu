@@ -179,9 +179,10 @@ __global__ void __launch_bounds__(256) cn_kernel(const int32_t *__restrict__ row
             }
         }
     }
+    // benign race: every writer stores the same value; test first so ~m writers per frame do not all hit one word
 #pragma unroll
     for (int v = 0; v < V; ++v)
-        if (act[v] && par[v]) st.unsat_iter[f + v] = iter + 1;        // benign race: every writer stores the same value
+        if (act[v] && par[v] && st.unsat_iter[f + v] != iter + 1) st.unsat_iter[f + v] = iter + 1;
     if (DEGMAX > 0) {
 #pragma unroll
         for (int k = 0; k < QN; ++k) {
