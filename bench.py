@@ -442,6 +442,24 @@ def run_extras(torch):
     except Exception as e:
         out["ldpc_dvbs2shape_64800_minsum_c4"] = {"error": repr(e)[:200]}
     try:
+        import helpers
+        from commpy_b200.links import ConvLinkGPU
+        from commpy_b200.modulation import QAMModem
+        link = ConvLinkGPU(helpers.k7(), QAMModem(256), frame_bits=4096, frames_per_batch=8192, decoding_type="soft", seed=4)
+        snr = 14.0 + 10 * np.log10(8 * 0.5)                          # Eb/N0 = 14 dB
+        msg, y, nv = link.make_batch(snr, 0, torch)
+        cnt = torch.zeros(3, dtype=torch.int64, device="cuda")
+        ms = timeit(lambda: link.receive_decode_count(msg, y, nv, cnt, torch), reps=3, warm=1)
+        nsym = y.numel()
+        out["c5_rx_chain_qam256_k7_soft"] = {
+            "value": nsym / ms * 1e3, "unit": "symbols/s", "ms": ms, "symbols": nsym,
+            "chain": "cpb_demod_soft -> cpb_viterbi_decode(soft) -> cpb_count_errors, symbols resident in HBM, 8192 frames of 4096 bits",
+            "roofline_frac": 12.0 * nsym / ms / 1e6 / peak}
+        del msg, y
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["c5_rx_chain_qam256_k7_soft"] = {"error": repr(e)[:200]}
+    try:
         from commpy_b200.modulation import QAMModem
         q = QAMModem(256)
         n = 1 << 24

@@ -1,0 +1,237 @@
+"""Monte-Carlo link simulation around the GPU decoding path (next row of SURVEY.md section 8f).
+
+* `LinkModel` / `link_performance` keep the reference's sequential, callable-driven loop and signature
+  (commpy/links.py:29-64, :269-342) -- host logic only, the callables it is given do the work (e.g. this
+  package's `Modem.demodulate` and `viterbi_decode`).
+* `AwgnSisoChannel` is the one channel convention the decoding path needs to synthesise its inputs
+  (commpy/channels.py:53,74: `noise_std = sqrt((isComplex+1)*nb_tx*Es / (rate*10^(SNR/10)))`, complex noise
+  `(N(0,1) + jN(0,1)) * noise_std * 0.5`).  Fading / MIMO channels are out of scope.
+* `ConvLinkGPU` is the batched form for config C5: random bits -> convolutional encoder -> Modem.modulate ->
+  AWGN, all generated on the device with torch, then THIS package's CUDA demapper, Viterbi decoder and error
+  counter; frames shard over ranks and the error counters are all-reduced so every rank takes the same
+  stop decision (`links.py:313`).
+"""
+import math
+from fractions import Fraction
+from inspect import getfullargspec
+
+import numpy as np
+
+from . import _lib, parallel
+
+__all__ = ["link_performance", "LinkModel", "AwgnSisoChannel", "ConvLinkGPU"]
+
+
+class AwgnSisoChannel:
+    """SISO AWGN channel with the reference's SNR convention (channels.py:37-93, :181-221 with fading (1+0j, 0))."""
+
+    nb_tx = 1
+    nb_rx = 1
+
+    def __init__(self, is_complex=True, rng=None):
+        self.isComplex = bool(is_complex)
+        self.noise_std = None
+        self.channel_gains = 1.0
+        self.rng = rng if rng is not None else np.random
+
+    def set_SNR_dB(self, SNR_dB, code_rate=1, Es=1):
+        self.noise_std = math.sqrt((self.isComplex + 1) * self.nb_tx * Es / (code_rate * 10 ** (SNR_dB / 10)))
+
+    def generate_noises(self, dims):
+        if self.isComplex:
+            return (self.rng.standard_normal(dims) + 1j * self.rng.standard_normal(dims)) * self.noise_std * 0.5
+        return self.rng.standard_normal(dims) * self.noise_std
+
+    def propagate(self, msg):
+        msg = np.asarray(msg)
+        self.channel_gains = np.ones(len(msg), dtype=complex if self.isComplex else float)
+        self.noises = self.generate_noises(len(msg))
+        self.unnoisy_output = msg
+        return msg + self.noises
+
+
+def link_performance(link_model, SNRs, send_max, err_min, send_chunk=None, code_rate=1):
+    """Same as `link_model.link_performance(...)` (links.py:29-64)."""
+    if not send_chunk:
+        send_chunk = err_min
+    return link_model.link_performance(SNRs, send_max, err_min, send_chunk, code_rate)
+
+
+class LinkModel:
+    """Link model built from callables, as in the reference (links.py:67-153):
+    `modulate(bits) -> symbols`, `channel` (set_SNR_dB / propagate / channel_gains / noise_std / nb_tx),
+    `receive(y, H, constellation, noise_var) -> bits or LLRs`, `decoder(array)` or the 6-argument form
+    `decoder(y, H, constellation, noise_var, array, bits_per_send)` chosen by arity (links.py:306)."""
+
+    def __init__(self, modulate, channel, receive, num_bits_symbol, constellation, Es=1, decoder=None, rate=Fraction(1, 1),
+                 number_chunks_per_send=1, stop_on_surpass_error=True):
+        self.modulate = modulate
+        self.channel = channel
+        self.receive = receive
+        self.num_bits_symbol = num_bits_symbol
+        self.constellation = constellation
+        self.Es = Es
+        self.rate = rate
+        self.number_chunks_per_send = number_chunks_per_send
+        self.stop_on_surpass_error = stop_on_surpass_error
+        self.decoder = (lambda msg: msg) if decoder is None else decoder
+        self.full_simulation_results = None
+
+    def link_performance(self, SNRs, send_max, err_min, send_chunk=None, code_rate=1):
+        """Sequential Monte-Carlo BER estimate, one chunk per iteration (links.py:269-342)."""
+        BERs = np.zeros_like(SNRs, dtype=float)
+        if send_chunk is None:
+            send_chunk = err_min
+        if type(code_rate) is float:
+            code_rate = Fraction(code_rate).limit_denominator(100)
+        self.rate = code_rate
+        divider = (Fraction(1, self.num_bits_symbol * self.channel.nb_tx) * 1 / code_rate).denominator
+        send_chunk = max(divider, send_chunk // divider * divider)
+        receive_size = self.channel.nb_tx * self.num_bits_symbol
+        full_args_decoder = len(getfullargspec(self.decoder).args) > 1
+        for i, snr in enumerate(SNRs):
+            self.channel.set_SNR_dB(snr, float(code_rate), self.Es)
+            bit_send = 0
+            bit_err = 0
+            while bit_send < send_max and bit_err < err_min:
+                msg = np.random.choice((0, 1), send_chunk)
+                y = self.channel.propagate(self.modulate(msg))
+                nv = self.channel.noise_std ** 2
+                if np.ndim(y) > 1:           # one received vector per channel use (MIMO-shaped channels)
+                    received = np.empty(int(math.ceil(len(msg) / float(self.rate))))
+                    for j in range(len(y)):
+                        received[receive_size * j:receive_size * (j + 1)] = \
+                            self.receive(y[j], self.channel.channel_gains[j], self.constellation, nv)
+                else:
+                    received = self.receive(y, self.channel.channel_gains, self.constellation, nv)
+                if full_args_decoder:
+                    decoded = self.decoder(y, self.channel.channel_gains, self.constellation, nv, received,
+                                           self.channel.nb_tx * self.num_bits_symbol)
+                else:
+                    decoded = self.decoder(received)
+                bit_err += np.bitwise_xor(msg, np.asarray(decoded)[:len(msg)].astype(int)).sum()
+                bit_send += send_chunk
+            BERs[i] = bit_err / bit_send
+            if bit_err < err_min:
+                break
+        return BERs
+
+
+def _ff_taps(trellis):
+    """Generator taps (delay 0 = current input) of a k=1 feed-forward shift-register trellis, or None."""
+    if trellis.k != 1:
+        return None
+    M, n = trellis.total_memory, trellis.n
+    nst, otab = np.asarray(trellis.next_state_table), np.asarray(trellis.output_table)
+    S = trellis.number_states
+    for s in range(S):
+        for u in range(2):
+            if nst[s, u] != ((u << (M - 1)) | (s >> 1)):
+                return None
+    taps = np.zeros((n, M + 1), dtype=np.int64)
+    for j in range(n):
+        taps[j, 0] = (otab[0, 1] >> (n - 1 - j)) & 1
+        for b in range(1, M + 1):
+            taps[j, b] = (otab[1 << (M - b), 0] >> (n - 1 - j)) & 1
+    for s in range(S):          # the code must be linear in (state, input) for the tap form to hold
+        for u in range(2):
+            regs = [u] + [(s >> (M - b)) & 1 for b in range(1, M + 1)]
+            sym = 0
+            for j in range(n):
+                sym = (sym << 1) | (int(np.dot(taps[j], regs)) & 1)
+            if sym != otab[s, u]:
+                return None
+    return taps
+
+
+class ConvLinkGPU:
+    """Batched convolutional-code link over AWGN on the GPU(s): TX chain in torch, RX chain in this package's CUDA.
+
+    Parameters: `trellis` (k=1 feed-forward, e.g. the K=7 (0o133,0o171) code), `modem` (commpy_b200 Modem),
+    `frame_bits` information bits per frame ('cont' termination), `frames_per_batch` frames decoded per step and rank.
+    """
+
+    def __init__(self, trellis, modem, frame_bits=4096, frames_per_batch=4096, decoding_type="soft", tb_depth=None, seed=0):
+        taps = _ff_taps(trellis)
+        if taps is None:
+            raise NotImplementedError("ConvLinkGPU generates frames on the device for k=1 feed-forward codes only")
+        if decoding_type not in ("soft", "hard"):
+            raise ValueError("decoding_type must be 'soft' or 'hard'")
+        self.trellis, self.modem, self.taps = trellis, modem, taps
+        self.frame_bits, self.frames = int(frame_bits), int(frames_per_batch)
+        self.decoding_type, self.tb_depth, self.seed = decoding_type, tb_depth, int(seed)
+        nb = modem.num_bits_symbol
+        if (trellis.n * self.frame_bits) % nb:
+            raise ValueError("frame_bits * n must be a multiple of the modem's bits per symbol")
+        self.rate = Fraction(trellis.k, trellis.n)
+
+    # -- TX chain on the device ---------------------------------------------------------------------
+    def _encode(self, msg, torch):
+        M = self.trellis.total_memory
+        n = self.trellis.n
+        pad = torch.nn.functional.pad(msg, (M, 0))
+        coded = torch.empty((msg.shape[0], n * msg.shape[1]), dtype=torch.uint8, device=msg.device)
+        for j in range(n):
+            acc = torch.zeros_like(msg)
+            for b in np.nonzero(self.taps[j])[0]:
+                acc ^= pad[:, M - b:M - b + msg.shape[1]]
+            coded[:, j::n] = acc
+        return coded
+
+    def make_batch(self, snr_db, batch_index, torch):
+        """(msg bits, received symbols, noise_var) for one batch of this rank -- everything stays on the device."""
+        rank, world, _ = parallel.world()
+        g = torch.Generator(device="cuda")
+        g.manual_seed(parallel.frame_seed(self.seed, batch_index * max(world, 1) + rank) % (1 << 62))
+        msg = torch.randint(0, 2, (self.frames, self.frame_bits), generator=g, device="cuda", dtype=torch.uint8)
+        coded = self._encode(msg, torch)
+        nb = self.modem.num_bits_symbol
+        w = (1 << torch.arange(nb - 1, -1, -1, device="cuda")).to(torch.int64)
+        idx = (coded.view(self.frames, -1, nb).to(torch.int64) * w).sum(-1)
+        cst = torch.as_tensor(np.asarray(self.modem.constellation, dtype=np.complex64), device="cuda")
+        x = cst[idx]
+        noise_std = math.sqrt(2 * self.modem.Es / (float(self.rate) * 10 ** (snr_db / 10)))       # channels.py:74
+        noise = torch.randn(x.shape + (2,), generator=g, device="cuda", dtype=torch.float32) * (noise_std * 0.5)
+        y = x + torch.view_as_complex(noise)
+        return msg, y, noise_std ** 2                                                              # links.py:329
+
+    # -- RX chain: this package's kernels -------------------------------------------------------------
+    def receive_decode_count(self, msg, y, noise_var, counters, torch):
+        import ctypes as C
+        from .channelcoding import viterbi_decode_batch
+        if self.decoding_type == "soft":
+            rx = self.modem.demodulate_batch(y, "soft", noise_var)
+        else:
+            rx = self.modem.demodulate_batch(y, "hard")
+        dec = viterbi_decode_batch(rx, self.trellis, self.tb_depth, self.decoding_type)
+        L = msg.shape[1]
+        rc = _lib.load().cpb_count_errors(_lib.ptr(dec), _lib.ptr(msg), C.c_int64(msg.shape[0]), C.c_int64(L),
+                                          C.c_int64(dec.shape[1]), C.c_int64(L), _lib.ptr(counters), _lib.stream_ptr(torch))
+        _lib.check(rc, "count_errors")
+        return dec
+
+    def link_performance(self, SNRs, send_max, err_min):
+        """BER per SNR (dB, `SNR = Eb/N0 + 10 log10(bits/symbol * rate)` as in the reference's examples).  A point ends
+        when the GLOBAL counters reach `err_min` errors or `send_max` bits; like the reference the sweep stops after
+        the first point that ends below `err_min` errors (links.py:339-341).  The stop rule is evaluated once per
+        batch (frames_per_batch * world_size frames), not once per frame."""
+        torch = _lib.require_cuda()
+        BERs = np.zeros(len(SNRs))
+        batch_index = 0
+        for i, snr in enumerate(SNRs):
+            tot = torch.zeros(3, dtype=torch.int64, device="cuda")          # bit errors, frame errors, bits sent
+            while True:
+                msg, y, nv = self.make_batch(float(snr), batch_index, torch)
+                batch_index += 1
+                local = torch.zeros(3, dtype=torch.int64, device="cuda")
+                self.receive_decode_count(msg, y, nv, local, torch)
+                local[2] = msg.numel()
+                parallel.allreduce_counters(local)
+                tot += local
+                c = tot.cpu().numpy()
+                if not parallel.stop_rule(c, send_max, err_min):
+                    break
+            BERs[i] = c[0] / c[2]
+            if c[0] < err_min:
+                break
+        return BERs

@@ -1,0 +1,96 @@
+"""Link-level tests: host loop (CPU) and the batched GPU chain (config C5 shape)."""
+import math
+
+import numpy as np
+import pytest
+
+import helpers
+from commpy_b200.links import AwgnSisoChannel, ConvLinkGPU, LinkModel, _ff_taps, link_performance
+
+
+def _q(x):
+    return 0.5 * math.erfc(x / math.sqrt(2))
+
+
+def test_linkmodel_host_loop_bpsk_matches_theory():
+    """commpy/tests/test_links.py:37-42 in spirit: uncoded antipodal signalling over real AWGN vs the Q function."""
+    np.random.seed(17121996)
+    ch = AwgnSisoChannel(is_complex=False, rng=np.random.RandomState(1))
+    model = LinkModel(lambda b: 2.0 * np.asarray(b) - 1.0, ch, lambda y, h, c, nv: (y > 0).astype(int), 1,
+                      np.array([-1.0, 1.0]), Es=1.0)
+    snrs = np.array([0.0, 4.0, 6.0])
+    bers = link_performance(model, snrs, 4e5, 600, 2000)
+    want = [_q(math.sqrt(10 ** (s / 10))) for s in snrs]       # noise_std^2 = Es/10^(SNR/10)
+    assert np.allclose(bers, want, rtol=0.25)
+    # arity sniffing (links.py:306): a 6-argument decoder is called with the full argument list
+    seen = {}
+
+    def dec6(y, h, c, nv, arr, bps):
+        seen["n"] = bps
+        return arr
+    model6 = LinkModel(lambda b: 2.0 * np.asarray(b) - 1.0, ch, lambda y, h, c, nv: (y > 0).astype(int), 1,
+                       np.array([-1.0, 1.0]), Es=1.0, decoder=dec6)
+    model6.link_performance(np.array([3.0]), 2000, 10, 1000)
+    assert seen["n"] == 1
+
+
+def test_ff_taps_and_chunk_rounding():
+    t = _ff_taps(helpers.k7())
+    assert t.shape == (2, 7)
+    assert int("".join(str(b) for b in t[0][::-1]), 2) == 0o133 and int("".join(str(b) for b in t[1][::-1]), 2) == 0o171
+    assert _ff_taps(helpers.rsc_k4()) is None          # recursive code: no tap form
+    # send_chunk is rounded down to a multiple of denominator(1/(bits*nb_tx)/rate) (links.py:302-303):
+    # 6 bits/symbol at rate 3/4 -> (1/6)/(3/4) = 2/9 -> chunks of 36 instead of 37
+    calls = []
+
+    def modulate(bits):
+        calls.append(len(bits))
+        return np.zeros(8, complex)
+    m = LinkModel(modulate, AwgnSisoChannel(rng=np.random.RandomState(0)), lambda y, h, c, nv: np.zeros(64, int), 6, None)
+    m.link_performance(np.array([0.0]), 100, 10 ** 9, 37, 0.75)
+    assert calls and set(calls) == {36}
+
+
+@pytest.mark.gpu
+def test_conv_link_gpu_qpsk_k7_soft_ber_and_oracle_agreement():
+    import torch
+    from oracle import oracle
+    from commpy_b200.modulation import QAMModem
+    tr = helpers.k7()
+    link = ConvLinkGPU(tr, QAMModem(4), frame_bits=1024, frames_per_batch=512, decoding_type="soft", seed=5)
+    ebn0 = np.array([2.0, 3.0])
+    bers = link.link_performance(ebn0 + 10 * math.log10(2 * 0.5), send_max=2e6, err_min=400)
+    # K=7 soft Viterbi: ~1.3e-3 at 2 dB and ~1.5e-4 at 3 dB (standard curve); loose statistical bounds
+    assert 4e-4 < bers[0] < 4e-3 and 2e-5 < bers[1] < 6e-4, bers
+    # the decoded bits of one batch agree with the CPU oracle fed the same LLRs
+    msg, y, nv = link.make_batch(float(ebn0[0]), 0, torch)
+    llr = link.modem.demodulate_batch(y, "soft", nv)
+    cnt = torch.zeros(3, dtype=torch.int64, device="cuda")
+    dec = link.receive_decode_count(msg, y, nv, cnt, torch).cpu().numpy()
+    want = oracle.viterbi_decode_batch(llr[:24].cpu().numpy().astype(np.float64), tr, None, "soft", threads=4)
+    assert (dec[:24] == want).mean() > 0.9999
+    assert int(cnt[0]) == int((dec != msg.cpu().numpy()).sum())
+
+
+@pytest.mark.gpu
+def test_dropin_linkmodel_with_gpu_receiver_and_decoder():
+    """commpy/examples/conv_encode_decode.py:99-127 shape: QPSK, (5,7) code, hard and unquantized Viterbi via LinkModel."""
+    from commpy_b200.channelcoding import Trellis, conv_encode, viterbi_decode
+    from commpy_b200.modulation import QAMModem
+    np.random.seed(3)
+    tr = Trellis(np.array([2]), np.array([[5, 7]]))
+    modem = QAMModem(4)
+    ch = AwgnSisoChannel(rng=np.random.RandomState(4))
+
+    def modulate(bits):
+        return modem.modulate(conv_encode(bits, tr, "cont"))
+
+    def receiver_hard(y, h, constellation, noise_var):
+        return modem.demodulate(y, "hard")
+
+    def decoder_hard(msg):
+        return viterbi_decode(msg, tr)
+
+    model = LinkModel(modulate, ch, receiver_hard, modem.num_bits_symbol, modem.constellation, modem.Es, decoder_hard, 0.5)
+    ber = model.link_performance(np.array([5.0]) + 10 * math.log10(2 * 0.5), 40000, 200, 1000, 0.5)[0]
+    assert 1e-4 < ber < 4e-3, ber                # commpy/channelcoding/README.md:159-160 quotes 7.8e-4 (hard, 5 dB)
