@@ -446,7 +446,7 @@ def run_extras(torch):
         from commpy_b200.links import ConvLinkGPU
         from commpy_b200.modulation import QAMModem
         link = ConvLinkGPU(helpers.k7(), QAMModem(256), frame_bits=4096, frames_per_batch=8192, decoding_type="soft", seed=4)
-        snr = 14.0 + 10 * np.log10(8 * 0.5)                          # Eb/N0 = 14 dB
+        snr = 14.0 + 10 * np.log10(8)                                # Eb/N0 = 14 dB (SNR = Eb/N0 + 10 log10(bits/symbol))
         msg, y, nv = link.make_batch(snr, 0, torch)
         cnt = torch.zeros(3, dtype=torch.int64, device="cuda")
         ms = timeit(lambda: link.receive_decode_count(msg, y, nv, cnt, torch), reps=3, warm=1)

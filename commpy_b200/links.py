@@ -211,7 +211,8 @@ class ConvLinkGPU:
         return dec
 
     def link_performance(self, SNRs, send_max, err_min):
-        """BER per SNR (dB, `SNR = Eb/N0 + 10 log10(bits/symbol * rate)` as in the reference's examples).  A point ends
+        """BER per SNR (dB, `SNR = Eb/N0 + 10 log10(bits/symbol)` as in the reference's examples,
+        conv_encode_decode.py:102; the code rate enters through `set_SNR_dB`, channels.py:74).  A point ends
         when the GLOBAL counters reach `err_min` errors or `send_max` bits; like the reference the sweep stops after
         the first point that ends below `err_min` errors (links.py:339-341).  The stop rule is evaluated once per
         batch (frames_per_batch * world_size frames), not once per frame."""

@@ -59,11 +59,12 @@ def test_conv_link_gpu_qpsk_k7_soft_ber_and_oracle_agreement():
     tr = helpers.k7()
     link = ConvLinkGPU(tr, QAMModem(4), frame_bits=1024, frames_per_batch=512, decoding_type="soft", seed=5)
     ebn0 = np.array([2.0, 3.0])
-    bers = link.link_performance(ebn0 + 10 * math.log10(2 * 0.5), send_max=2e6, err_min=400)
+    snr = ebn0 + 10 * math.log10(2)          # SNR = Eb/N0 + 10 log10(bits/symbol); set_SNR_dB divides by the rate itself
+    bers = link.link_performance(snr, send_max=2e6, err_min=400)
     # K=7 soft Viterbi: ~1.3e-3 at 2 dB and ~1.5e-4 at 3 dB (standard curve); loose statistical bounds
     assert 4e-4 < bers[0] < 4e-3 and 2e-5 < bers[1] < 6e-4, bers
     # the decoded bits of one batch agree with the CPU oracle fed the same LLRs
-    msg, y, nv = link.make_batch(float(ebn0[0]), 0, torch)
+    msg, y, nv = link.make_batch(float(snr[0]), 0, torch)
     llr = link.modem.demodulate_batch(y, "soft", nv)
     cnt = torch.zeros(3, dtype=torch.int64, device="cuda")
     dec = link.receive_decode_count(msg, y, nv, cnt, torch).cpu().numpy()
@@ -92,5 +93,5 @@ def test_dropin_linkmodel_with_gpu_receiver_and_decoder():
         return viterbi_decode(msg, tr)
 
     model = LinkModel(modulate, ch, receiver_hard, modem.num_bits_symbol, modem.constellation, modem.Es, decoder_hard, 0.5)
-    ber = model.link_performance(np.array([5.0]) + 10 * math.log10(2 * 0.5), 40000, 200, 1000, 0.5)[0]
+    ber = model.link_performance(np.array([5.0]) + 10 * math.log10(2), 40000, 200, 1000, 0.5)[0]
     assert 1e-4 < ber < 4e-3, ber                # commpy/channelcoding/README.md:159-160 quotes 7.8e-4 (hard, 5 dB)
