@@ -101,6 +101,7 @@ struct Params {
     int out_vec16;               // 1: rows of out are 16-byte aligned
     int in_aligned;              // 1: rows of coded are 4-byte (u8) / 16-byte (f32) aligned and n_in % 4 == 0
     uint32_t keep_mask;          // ~IDX_MASK, passed at run time so the key fix-up stays one LOP3 (reg & reg | imm)
+    int sm_count;
 };
 
 template <int PACK> struct KeyOps;
@@ -120,6 +121,13 @@ template <> struct KeyOps<1> {
     __device__ static __forceinline__ uint32_t min2(uint32_t a, uint32_t b) { return min(a, b); }
     __device__ static __forceinline__ uint32_t idx(int s) { return (uint32_t)s; }
 };
+
+__device__ __forceinline__ uint32_t mad_shift(uint32_t x, int sh, uint32_t acc)
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(1u << sh), "r"(acc));     // sh is a constant after unrolling
+    return r;
+}
 
 // one trellis step on register-resident keys: Kn <- ACS(K, Bm); W <- survivor bits; returns min key(s)
 template <class CODE, int PACK>
@@ -142,8 +150,9 @@ __device__ __forceinline__ uint32_t acs_step(const uint32_t (&K)[64], uint32_t (
         const uint32_t m1 = OPS::addmin(K[2 * l], Bm[CODE::out(2 * l, 1)], c11);
         Kn[l] = (m0 & keep) | OPS::idx(l);
         Kn[l + H] = (m1 & keep) | OPS::idx(l + H);
-        W[l >> WSH] += (m0 & OPS::LSB) << (l & ((1 << WSH) - 1));
-        W[(l + H) >> WSH] += (m1 & OPS::LSB) << (l & ((1 << WSH) - 1));
+        // survivor bit -> its slot in the word: one IMAD (x * 2^sh + W) on the FMA pipe, the ALU pipe is the busy one
+        W[l >> WSH] = mad_shift(m0 & OPS::LSB, l & ((1 << WSH) - 1), W[l >> WSH]);
+        W[(l + H) >> WSH] = mad_shift(m1 & OPS::LSB, l & ((1 << WSH) - 1), W[(l + H) >> WSH]);
     }
     // best state(s): lowest key = lowest metric, ties -> lowest state index (np.argmin, convcode.py:645)
     uint32_t r[22];
@@ -333,14 +342,16 @@ __device__ __noinline__ void tb_block(const Smem<PACK> sm, int ts, int te, int s
         if (FINAL) a64 |= (unsigned long long)sm.outbits[(lane + BD * fi) * 2 + 1] << 32;
         if (!((valid_mask >> fi) & 1)) continue;
         uint8_t *o = (fi == 0 ? out0 : out1) + p0;
-        if (!FINAL && out_vec16 && te - ts == TBB) {
-            const uint32_t b16 = (uint32_t)a64 & 0xffffu;
-            uint4 v;
-            v.x = (((b16 >> 0) & 15u) * 0x00204081u) & 0x01010101u;
-            v.y = (((b16 >> 4) & 15u) * 0x00204081u) & 0x01010101u;
-            v.z = (((b16 >> 8) & 15u) * 0x00204081u) & 0x01010101u;
-            v.w = (((b16 >> 12) & 15u) * 0x00204081u) & 0x01010101u;
-            *reinterpret_cast<uint4 *>(o) = v;
+        const int nbw = te - ts;
+        if (!FINAL && out_vec16 && (p0 & 7) == 0 && (nbw & 7) == 0) {
+            // 8 decoded bits -> 8 bytes per store (rows are 16-byte aligned, p0 is a multiple of 8)
+            for (int g8 = 0; g8 < nbw; g8 += 8) {
+                const uint32_t b8 = (uint32_t)(a64 >> g8) & 0xffu;
+                uint2 v;
+                v.x = (((b8 >> 0) & 15u) * 0x00204081u) & 0x01010101u;
+                v.y = (((b8 >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+                *reinterpret_cast<uint2 *>(o + g8) = v;
+            }
         } else {
             const int cnt = FINAL ? (L - p0) : (te - ts);
             for (int i = 0; i < cnt; ++i) o[i] = (uint8_t)((a64 >> i) & 1ull);
@@ -481,7 +492,11 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
     };
 
     int slot = 0;
-    int next_te = p.D - 2 + TBB;
+    // Traceback blocks end every TBB steps.  Warps that share an SM are put half a block out of phase (their CTA
+    // indices differ by multiples of the SM count) so that one warp's latency-bound traceback overlaps the
+    // other's add-compare-select instead of all warps of an SMSP stalling in the same step.
+    int ts_cur = p.D - 2;
+    int next_te = ts_cur + (((blockIdx.x / p.sm_count) & 1) ? TBB / 2 : TBB);
     uint32_t W[2 * PACK];
 
     auto finish_step = [&](int tau, uint32_t mn, uint32_t (&Kc)[64]) {
@@ -495,10 +510,11 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
             for (int s = 0; s < 64; ++s) Kc[s] -= sub;
         }
         if (tau == p.T) {
-            tb_block<CODE, PACK, true>(sm, next_te - TBB, tau, slot, p.D, p.L, outp[0], outp[PACK - 1], valid_mask, p.out_vec16);
+            tb_block<CODE, PACK, true>(sm, ts_cur, tau, slot, p.D, p.L, outp[0], outp[PACK - 1], valid_mask, p.out_vec16);
         } else if (tau == next_te) {
-            tb_block<CODE, PACK, false>(sm, next_te - TBB, tau, slot, p.D, p.L, outp[0], outp[PACK - 1], valid_mask, p.out_vec16);
-            next_te += TBB;
+            tb_block<CODE, PACK, false>(sm, ts_cur, tau, slot, p.D, p.L, outp[0], outp[PACK - 1], valid_mask, p.out_vec16);
+            ts_cur = tau;
+            next_te = tau + TBB;
         }
         slot = (slot + 1 == p.R) ? 0 : slot + 1;
     };
@@ -848,6 +864,7 @@ int cpb_viterbi_decode(const cpbTrellis *t, const void *coded_dev, int in_dtype,
         const int pack = (mode == CPB_VITERBI_HARD) ? 2 : 1;
         if (fast::smem_bytes(p.R, pack) > dp.smem_optin) { ws.release(); return CPB_EUNSUPPORTED; }
         p.keep_mask = (pack == 2) ? ~fast::KeyOps<2>::IDX_MASK : ~fast::KeyOps<1>::IDX_MASK;
+        p.sm_count = dp.sm_count > 0 ? dp.sm_count : 148;
         {
             const size_t row = (size_t)n_in * (pack == 2 ? 1 : 4), al = (pack == 2) ? 4 : 16;
             p.in_aligned = ((n_in % 4) == 0 && (row % al) == 0 && (((uintptr_t)coded_dev) % al) == 0) ? 1 : 0;

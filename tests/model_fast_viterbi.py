@@ -13,7 +13,7 @@ def out_sym(M, G0, G1, s, u):
     return ((bin(v & G0).count("1") & 1) << 1) | (bin(v & G1).count("1") & 1)
 
 
-def decode(coded, G0, G1, D=None, mode="hard", qmax=1 << 19, M=6, stats=None):
+def decode(coded, G0, G1, D=None, mode="hard", qmax=1 << 19, M=6, stats=None, first_block=TBB):
     S = 1 << M
     H = S // 2
     n_in = len(coded)
@@ -39,7 +39,8 @@ def decode(coded, G0, G1, D=None, mode="hard", qmax=1 << 19, M=6, stats=None):
     K = np.array([(0 if s == 0 else big) | s for s in range(S)], dtype=np.int64)
     otab = [[out_sym(M, G0, G1, s, u) for u in (0, 1)] for s in range(S)]
     slot = 0
-    next_te = D - 2 + TBB
+    ts_cur = D - 2
+    next_te = ts_cur + first_block          # the kernel starts odd CTAs half a block out of phase
 
     def tb_block(ts, te, final, slot_te):
         """Mirror of tb_block<> in viterbi.cu: walks keep a shift register `path` (low M bits = state, bit b =
@@ -122,10 +123,11 @@ def decode(coded, G0, G1, D=None, mode="hard", qmax=1 << 19, M=6, stats=None):
         assert Kn.max() < (1 << (16 if mode == "hard" else 32))
         K = Kn
         if tau == T:
-            tb_block(next_te - TBB, tau, True, slot)
+            tb_block(ts_cur, tau, True, slot)
         elif tau == next_te:
-            tb_block(next_te - TBB, tau, False, slot)
-            next_te += TBB
+            tb_block(ts_cur, tau, False, slot)
+            ts_cur = tau
+            next_te = tau + TBB
         slot = 0 if slot + 1 == R else slot + 1
     assert (out >= 0).all()
     return out
