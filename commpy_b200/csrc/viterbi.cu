@@ -343,7 +343,15 @@ __device__ __noinline__ void tb_block(const Smem<PACK> sm, int ts, int te, int s
         if (!((valid_mask >> fi) & 1)) continue;
         uint8_t *o = (fi == 0 ? out0 : out1) + p0;
         const int nbw = te - ts;
-        if (!FINAL && out_vec16 && (p0 & 7) == 0 && (nbw & 7) == 0) {
+        if (!FINAL && out_vec16 && (p0 & 15) == 0 && nbw == 16) {
+            const uint32_t b16 = (uint32_t)a64 & 0xffffu;
+            uint4 v;
+            v.x = (((b16 >> 0) & 15u) * 0x00204081u) & 0x01010101u;
+            v.y = (((b16 >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+            v.z = (((b16 >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+            v.w = (((b16 >> 12) & 15u) * 0x00204081u) & 0x01010101u;
+            *reinterpret_cast<uint4 *>(o) = v;
+        } else if (!FINAL && out_vec16 && (p0 & 7) == 0 && (nbw & 7) == 0) {
             // 8 decoded bits -> 8 bytes per store (rows are 16-byte aligned, p0 is a multiple of 8)
             for (int g8 = 0; g8 < nbw; g8 += 8) {
                 const uint32_t b8 = (uint32_t)(a64 >> g8) & 0xffu;
@@ -492,11 +500,10 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
     };
 
     int slot = 0;
-    // Traceback blocks end every TBB steps.  Warps that share an SM are put half a block out of phase (their CTA
-    // indices differ by multiples of the SM count) so that one warp's latency-bound traceback overlaps the
-    // other's add-compare-select instead of all warps of an SMSP stalling in the same step.
+    // Traceback blocks end every TBB steps.  (Starting alternate warps half a block out of phase was measured and
+    // changes nothing: warps drift apart on their own.)
     int ts_cur = p.D - 2;
-    int next_te = ts_cur + (((blockIdx.x / p.sm_count) & 1) ? TBB / 2 : TBB);
+    int next_te = ts_cur + TBB;
     uint32_t W[2 * PACK];
 
     auto finish_step = [&](int tau, uint32_t mn, uint32_t (&Kc)[64]) {
