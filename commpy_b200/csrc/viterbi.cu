@@ -89,6 +89,10 @@ constexpr int QBITS = 19;          // |quantised LLR| <= 2^19
 constexpr int QMAX = 1 << QBITS;
 constexpr int BD = 32;             // one warp per CTA: every synchronisation below is a __syncwarp()
 constexpr int QD = 4;              // input prefetch distance, in pairs of trellis steps
+#ifndef CPB_ARITH_BITS
+#define CPB_ARITH_BITS 0
+#endif
+constexpr bool ARITH_BITS = CPB_ARITH_BITS != 0;
 
 struct Params {
     const void *coded;
@@ -150,9 +154,21 @@ __device__ __forceinline__ uint32_t acs_step(const uint32_t (&K)[64], uint32_t (
         const uint32_t m1 = OPS::addmin(K[2 * l], Bm[CODE::out(2 * l, 1)], c11);
         Kn[l] = (m0 & keep) | OPS::idx(l);
         Kn[l + H] = (m1 & keep) | OPS::idx(l + H);
-        // survivor bit -> its slot in the word: one IMAD (x * 2^sh + W) on the FMA pipe, the ALU pipe is the busy one
-        W[l >> WSH] = mad_shift(m0 & OPS::LSB, l & ((1 << WSH) - 1), W[l >> WSH]);
-        W[(l + H) >> WSH] = mad_shift(m1 & OPS::LSB, l & ((1 << WSH) - 1), W[(l + H) >> WSH]);
+        // survivor bit = LSB of the winner.  Instead of masking it out (LOP3: ALU pipe only, and the ALU pipe is the
+        // busy one) it is recovered with adds the scheduler may place on either pipe: the winner's index field is
+        // 2l+d, the refreshed key's is l (resp. l+H), the metric fields are equal, so per 16/32-bit lane
+        //   m0 - Kn[l] - l = d        and        (m1 + (H - l)) - Kn[l+H] = d      (no borrow between lanes).
+        uint32_t x0, x1;
+        if (ARITH_BITS) {
+            x0 = (m0 - Kn[l]) - OPS::idx(l);
+            x1 = (m1 + OPS::idx(H - l)) - Kn[l + H];
+        } else {
+            x0 = m0 & OPS::LSB;
+            x1 = m1 & OPS::LSB;
+        }
+        // survivor bit -> its slot in the word: one IMAD (x * 2^sh + W) on the FMA pipe
+        W[l >> WSH] = mad_shift(x0, l & ((1 << WSH) - 1), W[l >> WSH]);
+        W[(l + H) >> WSH] = mad_shift(x1, l & ((1 << WSH) - 1), W[(l + H) >> WSH]);
     }
     // best state(s): lowest key = lowest metric, ties -> lowest state index (np.argmin, convcode.py:645)
     uint32_t r[22];
