@@ -546,21 +546,26 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
 #pragma unroll
     for (int i = 0; i < QD; ++i) qd[i] = load_pair(i);
     const int npairs = (p.T + 1) >> 1;
+    // branch metrics are produced one step ahead of the add-compare-select that uses them, so the look-up table
+    // read (hard) / float->fixed conversion (soft) of step tau+1 overlaps the ~400 instructions of step tau
+    uint32_t BmA[4], BmB[4];
+    make_bm(qd[0], 0, BmA);
     for (int pr = 0; pr < npairs; ++pr) {
         const Raw cur = qd[0];
 #pragma unroll
         for (int i = 0; i + 1 < QD; ++i) qd[i] = qd[i + 1];
         qd[QD - 1] = load_pair(pr + QD);            // software prefetch, QD pairs of steps ahead
         const int tau = 2 * pr + 1;
-        uint32_t Bm[4];
-        make_bm(cur, 0, Bm);
-        uint32_t mn = acs_step<CODE, PACK>(K, Kn, Bm, W, keep);
+        if (PACK == 2) make_bm(cur, 1, BmB);        // (the soft kernel is register-capped: it converts in place)
+        uint32_t mn = acs_step<CODE, PACK>(K, Kn, BmA, W, keep);
         finish_step(tau, mn, Kn);
+        if (PACK != 2) make_bm(cur, 1, BmB);
+        if (PACK == 2) make_bm(qd[0], 0, BmA);
         if (tau + 1 <= p.T) {
-            make_bm(cur, 1, Bm);
-            mn = acs_step<CODE, PACK>(Kn, K, Bm, W, keep);
+            mn = acs_step<CODE, PACK>(Kn, K, BmB, W, keep);
             finish_step(tau + 1, mn, K);
         }
+        if (PACK != 2) make_bm(qd[0], 0, BmA);
     }
 }
 
