@@ -19,7 +19,7 @@ SYMBOLS = [
     "cpb_trellis_create", "cpb_trellis_destroy", "cpb_trellis_fast_path",
     "cpb_viterbi_sizes", "cpb_viterbi_workspace_bytes", "cpb_viterbi_decode", "cpb_viterbi_decode_host",
     "cpb_map_decode", "cpb_turbo_decode",
-    "cpb_ldpc_create", "cpb_ldpc_destroy", "cpb_ldpc_workspace_bytes", "cpb_ldpc_minsum",
+    "cpb_ldpc_create", "cpb_ldpc_destroy", "cpb_ldpc_workspace_bytes", "cpb_ldpc_minsum", "cpb_ldpc_sumproduct",
     "cpb_modem_create", "cpb_modem_destroy", "cpb_modem_is_separable", "cpb_demod_soft", "cpb_demod_hard",
     "cpb_count_errors",
 ]

@@ -99,8 +99,10 @@ def _ldpc_handle(ldpc_code_params):
     return cache[dev][0].ptr, cache[dev][1]
 
 
-def ldpc_bp_decode_batch(llr, ldpc_code_params, n_iters, precision="fp32", return_llrs=True, return_iters=False):
-    """Min-sum BP on a (batch, n_vnodes) array of LLRs (reference sign convention: bit = signbit(llr)).
+def ldpc_bp_decode_batch(llr, ldpc_code_params, n_iters, precision="fp32", return_llrs=True, return_iters=False,
+                         decoder_algorithm="MSA"):
+    """Min-sum ('MSA') or sum-product ('SPA') BP on a (batch, n_vnodes) array of LLRs (reference sign convention:
+    bit = signbit(llr)).
 
     llr : torch CUDA tensor (float32 for 'fp32', float64 for 'fp64' -- clipped IN PLACE to +-500) or numpy array.
     Returns dec (batch, n) uint8 [, out_llrs (batch, n)] [, iterations (batch,) int32] as torch CUDA tensors.
@@ -120,7 +122,10 @@ def ldpc_bp_decode_batch(llr, ldpc_code_params, n_iters, precision="fp32", retur
     dec = torch.empty((batch, n), dtype=torch.uint8, device=x.device)
     out = torch.empty_like(x) if return_llrs else None
     iters = torch.empty((batch,), dtype=torch.int32, device=x.device) if return_iters else None
-    rc = _lib.load().cpb_ldpc_minsum(handle, _lib.ptr(x), _lib.LDPC_FP64 if precision == "fp64" else _lib.LDPC_FP32,
+    if decoder_algorithm not in ("MSA", "SPA"):
+        raise NameError('Please input a valid decoder_algorithm string (meanning "SPA" or "MSA").')
+    fn = _lib.load().cpb_ldpc_minsum if decoder_algorithm == "MSA" else _lib.load().cpb_ldpc_sumproduct
+    rc = fn(handle, _lib.ptr(x), _lib.LDPC_FP64 if precision == "fp64" else _lib.LDPC_FP32,
                                      C.c_int64(batch), int(n_iters), _lib.ptr(dec), _lib.ptr(out), _lib.ptr(iters),
                                      C.c_void_p(0), C.c_size_t(0), _lib.stream_ptr(torch))
     _lib.check(rc, "ldpc_bp_decode")
@@ -133,24 +138,23 @@ def ldpc_bp_decode_batch(llr, ldpc_code_params, n_iters, precision="fp32", retur
 
 
 def ldpc_bp_decode(llr_vec, ldpc_code_params, decoder_algorithm, n_iters, precision="fp64"):
-    """Drop-in for commpy.channelcoding.ldpc_bp_decode (ldpc.py:144-254), 'MSA' algorithm.
+    """Drop-in for commpy.channelcoding.ldpc_bp_decode (ldpc.py:144-254), 'MSA' and 'SPA' algorithms.
 
     `llr_vec` (1-D, one or several blocks back to back) is clipped in place to +-500 like the reference
     (:186).  With the default precision='fp64' the GPU reproduces the float64 reference bit for bit
     (decisions AND out_llrs); precision='fp32' is the throughput mode.  Returns (dec_word int8, out_llrs) with
-    one block per column, squeezed (:251-254).  'SPA' is not built yet (NotImplementedError); any other name
-    raises NameError as the reference does (:239-240).
+    one block per column, squeezed (:251-254).  'SPA' (sum-product, :209-227) agrees with the reference to rounding
+    (~1e-12 on out_llrs in fp64), 'MSA' exactly; any other name raises NameError as the reference does (:239-240).
     """
-    if decoder_algorithm == "SPA":
-        raise NotImplementedError("the sum-product variant is not part of the B200 path yet; use 'MSA'")
-    if decoder_algorithm != "MSA":
+    if decoder_algorithm not in ("MSA", "SPA"):
         raise NameError('Please input a valid decoder_algorithm string (meanning "SPA" or "MSA").')
     llr_vec = np.asarray(llr_vec) if not isinstance(llr_vec, np.ndarray) else llr_vec
     if np.issubdtype(llr_vec.dtype, np.floating):
         llr_vec.clip(-_llr_max, _llr_max, llr_vec)            # in place, ldpc.py:186
     _, n = _ldpc_handle(ldpc_code_params)
     n_blocks = llr_vec.size // n
-    dec, out = ldpc_bp_decode_batch(llr_vec.reshape(n_blocks, n), ldpc_code_params, n_iters, precision)
+    dec, out = ldpc_bp_decode_batch(llr_vec.reshape(n_blocks, n), ldpc_code_params, n_iters, precision,
+                                    decoder_algorithm=decoder_algorithm)
     dec_word = dec.cpu().numpy().reshape(-1).reshape(-1, n_blocks, order="F").squeeze().astype(np.int8)
     out_llrs = out.cpu().numpy().astype(np.float64).reshape(-1).reshape(-1, n_blocks, order="F").squeeze()
     return dec_word, out_llrs

@@ -222,6 +222,61 @@ __global__ void __launch_bounds__(256) cn_kernel(const int32_t *__restrict__ row
     }
 }
 
+// Sum-product check node (ldpc.py:209-227): t = tanh(Q/2), R_ij = 2 atanh(clip((prod_row t) / t_ij, -1, 1)) clipped to
+// +-500.  Same formula as the reference (product of the whole row divided by the edge's own factor); the product is
+// formed directly instead of through exp2(sum(log2(complex))) so results agree to rounding (~1e-13), not bit for bit.
+template <typename T>
+__global__ void __launch_bounds__(256) cn_spa_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
+                                                     int m, int64_t F, int iter, const T *__restrict__ post,
+                                                     T *__restrict__ R, const State st)
+{
+    using VT = typename VecOf<T>::type;
+    constexpr int V = VecOf<T>::V;
+    const int64_t G = F / V;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)m * G) return;
+    const int i = (int)(gid / G);
+    const int64_t f = (gid - (int64_t)i * G) * V;
+    bool act[V];
+    bool any = false;
+#pragma unroll
+    for (int v = 0; v < V; ++v) { act[v] = st.done[f + v] == 0; any |= act[v]; }
+    if (!any) return;
+    const int e0 = __ldg(&row_ptr[i]), e1 = __ldg(&row_ptr[i + 1]);
+    T prod[V];
+    int par[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { prod[v] = (T)1; par[v] = 0; }
+    for (int e = e0; e < e1; ++e) {
+        const int c = __ldg(&col_idx[e]);
+        const VT p = *reinterpret_cast<const VT *>(post + (int64_t)c * F + f);
+        const VT r = *reinterpret_cast<const VT *>(R + (int64_t)e * F + f);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            par[v] ^= signbit(p.v[v]) ? 1 : 0;
+            prod[v] *= tanh((p.v[v] - r.v[v]) * (T)0.5);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+        if (act[v] && par[v] && st.unsat_iter[f + v] != iter + 1) st.unsat_iter[f + v] = iter + 1;
+    for (int e = e0; e < e1; ++e) {
+        const int c = __ldg(&col_idx[e]);
+        const VT p = *reinterpret_cast<const VT *>(post + (int64_t)c * F + f);
+        VT r = *reinterpret_cast<const VT *>(R + (int64_t)e * F + f);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const T t = tanh((p.v[v] - r.v[v]) * (T)0.5);
+            T x = ((T)1 / t) * prod[v];
+            x = x > (T)1 ? (T)1 : (x < (T)-1 ? (T)-1 : x);           // NaN (a zero LLR in the row) passes through, as in numpy
+            x = atanh(x) * (T)2;
+            x = x > (T)500 ? (T)500 : (x < (T)-500 ? (T)-500 : x);
+            if (act[v]) r.v[v] = x;
+        }
+        *reinterpret_cast<VT *>(R + (int64_t)e * F + f) = r;
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) vn_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ col_edge,
                                                  int n, int64_t F, int iter, const T *__restrict__ llrT,
@@ -288,7 +343,7 @@ static int64_t chunk_frames(const cpbLdpc *h, int64_t batch)
 }
 
 template <typename T>
-static int run(const cpbLdpc *h, T *llr, int64_t batch, int n_iters, uint8_t *dec, T *out_llr, int32_t *iters_out,
+static int run(const cpbLdpc *h, T *llr, int64_t batch, int n_iters, int spa, uint8_t *dec, T *out_llr, int32_t *iters_out,
                void *workspace, size_t workspace_bytes, cudaStream_t st)
 {
     constexpr int V = VecOf<T>::V;
@@ -317,7 +372,8 @@ static int run(const cpbLdpc *h, T *llr, int64_t batch, int n_iters, uint8_t *de
         const unsigned cn_blocks = (unsigned)ceil_div((int64_t)h->m * G, 256);
         const unsigned vn_blocks = (unsigned)ceil_div((int64_t)h->n * G, 256);
         for (int it = 0; it < n_iters; ++it) {
-            if (h->max_row_deg <= 8) cn_kernel<T, 8><<<cn_blocks, 256, 0, st>>>(h->row_ptr, h->col_idx, h->m, F, it, post, R, s);
+            if (spa) cn_spa_kernel<T><<<cn_blocks, 256, 0, st>>>(h->row_ptr, h->col_idx, h->m, F, it, post, R, s);
+            else if (h->max_row_deg <= 8) cn_kernel<T, 8><<<cn_blocks, 256, 0, st>>>(h->row_ptr, h->col_idx, h->m, F, it, post, R, s);
             else cn_kernel<T, 0><<<cn_blocks, 256, 0, st>>>(h->row_ptr, h->col_idx, h->m, F, it, post, R, s);
             vn_kernel<T><<<vn_blocks, 256, 0, st>>>(h->col_ptr, h->col_edge, h->n, F, it, llrT, R, post, s);
         }
@@ -397,19 +453,34 @@ int cpb_ldpc_workspace_bytes(const cpbLdpc *h, int64_t batch, int precision, siz
     return CPB_OK;
 }
 
-int cpb_ldpc_minsum(const cpbLdpc *h, void *llr_dev, int precision, int64_t batch, int n_iters, uint8_t *dec_dev,
-                    void *out_llr_dev, int32_t *iters_dev, void *workspace_dev, size_t workspace_bytes, void *stream)
+static int ldpc_dispatch(const cpbLdpc *h, void *llr_dev, int precision, int64_t batch, int n_iters, int spa,
+                         uint8_t *dec_dev, void *out_llr_dev, int32_t *iters_dev, void *workspace_dev,
+                         size_t workspace_bytes, void *stream)
 {
     if (!h || !llr_dev || !dec_dev || batch < 0 || n_iters < 0) return CPB_EINVAL;
     if (batch == 0) return CPB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == CPB_LDPC_FP64)
-        return ldpc::run<double>(h, reinterpret_cast<double *>(llr_dev), batch, n_iters, dec_dev,
+        return ldpc::run<double>(h, reinterpret_cast<double *>(llr_dev), batch, n_iters, spa, dec_dev,
                                  reinterpret_cast<double *>(out_llr_dev), iters_dev, workspace_dev, workspace_bytes, st);
     if (precision == CPB_LDPC_FP32)
-        return ldpc::run<float>(h, reinterpret_cast<float *>(llr_dev), batch, n_iters, dec_dev,
+        return ldpc::run<float>(h, reinterpret_cast<float *>(llr_dev), batch, n_iters, spa, dec_dev,
                                 reinterpret_cast<float *>(out_llr_dev), iters_dev, workspace_dev, workspace_bytes, st);
     return CPB_EINVAL;
+}
+
+int cpb_ldpc_minsum(const cpbLdpc *h, void *llr_dev, int precision, int64_t batch, int n_iters, uint8_t *dec_dev,
+                    void *out_llr_dev, int32_t *iters_dev, void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    return ldpc_dispatch(h, llr_dev, precision, batch, n_iters, 0, dec_dev, out_llr_dev, iters_dev, workspace_dev,
+                         workspace_bytes, stream);
+}
+
+int cpb_ldpc_sumproduct(const cpbLdpc *h, void *llr_dev, int precision, int64_t batch, int n_iters, uint8_t *dec_dev,
+                        void *out_llr_dev, int32_t *iters_dev, void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    return ldpc_dispatch(h, llr_dev, precision, batch, n_iters, 1, dec_dev, out_llr_dev, iters_dev, workspace_dev,
+                         workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -112,6 +112,13 @@ int cpb_ldpc_minsum(const cpbLdpc *h, void *llr_dev, int precision, int64_t batc
                     uint8_t *dec_dev, void *out_llr_dev, int32_t *iters_dev,
                     void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* Sum-product variant ('SPA', ldpc.py:209-227): same arguments and schedule; check-node rule
+ * R_ij = 2 atanh(clip(prod_row tanh(Q/2) / tanh(Q_ij/2), -1, 1)), clipped to +-500.  Agrees with the reference to
+ * rounding (the reference forms the product through complex log2/exp2), not bit for bit. */
+int cpb_ldpc_sumproduct(const cpbLdpc *h, void *llr_dev, int precision, int64_t batch, int n_iters,
+                        uint8_t *dec_dev, void *out_llr_dev, int32_t *iters_dev,
+                        void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* ---- Soft / hard demapper: commpy/modulation.py:100-141 Modem.demodulate ------------------------ */
 typedef struct cpbModem cpbModem;
 /* constellation: M complex points as interleaved (re, im) float64 host values, index k <-> bits MSB first. */

@@ -355,9 +355,26 @@ static double orc_sign(double x) { return (x > 0.0) - (x < 0.0); }   /* np.sign;
  * dec: nblocks*n int8 (block-major; the Python wrapper does the order='F' reshape of :251-254).
  * out_llr: nblocks*n doubles.  iters_done (nullable): per block, iterations executed.
  */
+static int orc_ldpc_bp(double *llr, int64_t nblocks, int n, int m, const int32_t *row_ptr, const int32_t *col_idx,
+                      int n_iters, int spa, int8_t *dec, double *out_llr, int32_t *iters_done);
+
 int orc_ldpc_minsum(double *llr, int64_t nblocks, int n, int m,
                     const int32_t *row_ptr, const int32_t *col_idx,
                     int n_iters, int8_t *dec, double *out_llr, int32_t *iters_done)
+{
+    return orc_ldpc_bp(llr, nblocks, n, m, row_ptr, col_idx, n_iters, 0, dec, out_llr, iters_done);
+}
+
+/* sum-product variant: ldpc.py:209-227 */
+int orc_ldpc_sumproduct(double *llr, int64_t nblocks, int n, int m,
+                        const int32_t *row_ptr, const int32_t *col_idx,
+                        int n_iters, int8_t *dec, double *out_llr, int32_t *iters_done)
+{
+    return orc_ldpc_bp(llr, nblocks, n, m, row_ptr, col_idx, n_iters, 1, dec, out_llr, iters_done);
+}
+
+static int orc_ldpc_bp(double *llr, int64_t nblocks, int n, int m, const int32_t *row_ptr, const int32_t *col_idx,
+                      int n_iters, int spa, int8_t *dec, double *out_llr, int32_t *iters_done)
 {
     const int nnz = row_ptr[m];
     for (int64_t i = 0; i < nblocks * n; ++i) {                                     /* :186 */
@@ -387,6 +404,29 @@ int orc_ldpc_minsum(double *llr, int64_t nblocks, int n, int m,
                 if (par) ok = 0;
             }
             if (ok) break;
+            if (spa) {
+                for (int i = 0; i < m; ++i) {                                       /* :209-227 */
+                    int b0 = row_ptr[i], deg = row_ptr[i + 1] - row_ptr[i];
+                    double lsum = 0.0; int negs = 0;
+                    for (int j = 0; j < deg; ++j) {
+                        double t = tanh(msg[b0 + j] * .5);                          /* :211-212 */
+                        msg[b0 + j] = t;
+                        lsum += log2(fabs(t));                                      /* real part of log2(complex t), :217-218 */
+                        if (t < 0.0) negs++;
+                    }
+                    double prod = exp2(lsum);                                       /* :219: exp2(sum).real = +-2^Re */
+                    if (negs & 1) prod = -prod;
+                    for (int j = 0; j < deg; ++j) {
+                        double v = (1.0 / msg[b0 + j]) * prod;                      /* :222-223 */
+                        if (v > 1.0) v = 1.0;
+                        if (v < -1.0) v = -1.0;                                     /* :224 (NaN passes through) */
+                        v = atanh(v) * 2.0;                                         /* :225-226 */
+                        if (v > 500.0) v = 500.0;
+                        if (v < -500.0) v = -500.0;                                 /* :227 */
+                        msg[b0 + j] = v;
+                    }
+                }
+            } else
             for (int i = 0; i < m; ++i) {                                           /* :230-238 */
                 int b0 = row_ptr[i], deg = row_ptr[i + 1] - row_ptr[i];
                 for (int j = 0; j < deg; ++j) tmp[j] = msg[b0 + j];

@@ -46,7 +46,7 @@ def lib():
         build()
         _lib = C.CDLL(_SO)
         for name in ("orc_viterbi_decode", "orc_viterbi_decode_batch", "orc_map_decode", "orc_turbo_decode",
-                     "orc_turbo_decode_batch", "orc_ldpc_minsum", "orc_demod_soft", "orc_demod_hard"):
+                     "orc_turbo_decode_batch", "orc_ldpc_minsum", "orc_ldpc_sumproduct", "orc_demod_soft", "orc_demod_hard"):
             getattr(_lib, name).restype = C.c_int
     return _lib
 
@@ -182,9 +182,9 @@ def csr_from_params(ldpc_code_params):
 
 
 def ldpc_bp_decode(llr_vec, ldpc_code_params, decoder_algorithm, n_iters, return_iters=False, threads=1):
-    """MSA only.  llr_vec is clipped in place like the reference (ldpc.py:186) when it is a float64 array."""
-    if decoder_algorithm != "MSA":
-        raise NotImplementedError("oracle restates the MSA branch only")
+    """'MSA' or 'SPA'.  llr_vec is clipped in place like the reference (ldpc.py:186) when it is a float64 array."""
+    if decoder_algorithm not in ("MSA", "SPA"):
+        raise NameError('Please input a valid decoder_algorithm string (meanning "SPA" or "MSA").')
     row_ptr, col_idx, m, n = csr_from_params(ldpc_code_params)
     if isinstance(llr_vec, np.ndarray) and llr_vec.dtype == np.float64 and llr_vec.flags.c_contiguous:
         llr = llr_vec
@@ -194,7 +194,7 @@ def ldpc_bp_decode(llr_vec, ldpc_code_params, decoder_algorithm, n_iters, return
     dec = np.zeros(n_blocks * n, dtype=np.int8)
     out = np.zeros(n_blocks * n, dtype=np.float64)
     iters = np.zeros(n_blocks, dtype=np.int32)
-    fn = lib().orc_ldpc_minsum
+    fn = lib().orc_ldpc_minsum if decoder_algorithm == "MSA" else lib().orc_ldpc_sumproduct
     flat = llr.reshape(-1)
 
     def run(lo, hi):

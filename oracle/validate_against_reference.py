@@ -189,8 +189,30 @@ def main():
         ld[key + "_indices"] = H.indices.astype(np.int32)
         ld[key + "_meta"] = np.array([rel, str(nblk), str(iters), str(H.shape[0]), str(H.shape[1])])
         case += 1
+    # sum-product variant (ldpc.py:209-227): decisions equal, out_llrs to 1e-9 (the reference goes through complex log2/exp2)
+    scase = 0
+    for rel, nblk, iters, eb in (("gallager/96.33.964.txt", 2, 20, 2.5), ("wimax/1440.720.txt", 1, 8, 1.5),
+                                 ("wimax/960.720.a.txt", 1, 6, 3.0)):
+        params = rcc.get_ldpc_code_params(os.path.join(ddir, rel), compute_matrix=True)
+        n = params["n_vnodes"]
+        rate = 1.0 - params["n_cnodes"] / n
+        sigma = 1.0 / np.sqrt(2 * rate * 10 ** (eb / 10))
+        llr = 2.0 * (1.0 + sigma * rs.randn(n * nblk)) / sigma ** 2
+        a, b = llr.copy(), llr.copy()
+        with np.errstate(all="ignore"):
+            dr, lr = rcc.ldpc_bp_decode(a, params, "SPA", iters)
+        do, lo = oracle.ldpc_bp_decode(b, params, "SPA", iters)
+        assert np.array_equal(dr, do), ("ldpc spa dec", rel)
+        assert np.allclose(lr, lo, rtol=1e-9, atol=1e-9), ("ldpc spa llr", rel)
+        H = params["parity_check_matrix"].tocsr()
+        H.sort_indices()
+        key = "s%02d" % scase
+        ld[key + "_llr"], ld[key + "_dec"], ld[key + "_out"] = llr, dr, lr
+        ld[key + "_indptr"], ld[key + "_indices"] = H.indptr.astype(np.int32), H.indices.astype(np.int32)
+        ld[key + "_meta"] = np.array([rel, str(nblk), str(iters), str(H.shape[0]), str(H.shape[1])])
+        scase += 1
     np.savez_compressed(os.path.join(GOLD, "ldpc.npz"), **ld)
-    print("ldpc_bp_decode MSA: %d cases exact incl. out_llrs (%.0fs)" % (case, time.time() - t_start))
+    print("ldpc_bp_decode MSA: %d cases exact incl. out_llrs, SPA: %d cases (%.0fs)" % (case, scase, time.time() - t_start))
 
     # ---------------- demapper ----------------
     dm = {}

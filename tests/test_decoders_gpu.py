@@ -285,3 +285,20 @@ def test_map_decode_unaligned_length_scalar_path():
         L, _ = map_decode(ys, yp, tr, s2, La, "decode")
         Lo, _ = oracle.map_decode(ys, yp, tr, s2, La, "decode")
         assert (np.abs(L - Lo) <= MAP_ATOL + MAP_RTOL * np.abs(Lo)).all(), (N, float(np.abs(L - Lo).max()))
+
+
+def test_ldpc_spa_matches_reference_golden():
+    """'SPA' (ldpc.py:209-227) in fp64: same decisions, out_llrs to 1e-6 (formula identical, rounding differs)."""
+    import scipy.sparse as sp
+    g = np.load(os.path.join(GOLD, "ldpc.npz"))
+    for c in range(3):
+        rel, nblk, iters, m, n = g["s%02d_meta" % c]
+        H = sp.csr_matrix((np.ones(len(g["s%02d_indices" % c]), np.int8), g["s%02d_indices" % c], g["s%02d_indptr" % c]),
+                          shape=(int(m), int(n)))
+        params = {"n_vnodes": int(n), "n_cnodes": int(m), "parity_check_matrix": H.tocsc()}
+        dec, out = ldpc_bp_decode(g["s%02d_llr" % c].copy(), params, "SPA", int(iters))
+        assert np.array_equal(dec, g["s%02d_dec" % c]), rel
+        assert np.allclose(out, g["s%02d_out" % c], rtol=1e-6, atol=1e-6), (rel, float(np.abs(out - g["s%02d_out" % c]).max()))
+    # fp32 throughput mode: decisions of converged blocks agree
+    dec32, _ = ldpc_bp_decode(g["s00_llr"].copy(), _golden_ldpc(0)[1], "SPA", 20, precision="fp32")
+    assert (dec32 == g["s00_dec"]).mean() > 0.99

@@ -97,3 +97,16 @@ def test_oracle_threads_agree():
     a = oracle.viterbi_decode_batch(x, t, None, "hard", threads=1)
     b = oracle.viterbi_decode_batch(x, t, None, "hard", threads=4)
     assert np.array_equal(a, b)
+
+
+def test_ldpc_spa_golden():
+    import scipy.sparse as sp
+    g = np.load(os.path.join(GOLD, "ldpc.npz"))
+    for c in range(3):
+        rel, nblk, iters, m, n = g["s%02d_meta" % c]
+        H = sp.csr_matrix((np.ones(len(g["s%02d_indices" % c]), np.int8), g["s%02d_indices" % c], g["s%02d_indptr" % c]),
+                          shape=(int(m), int(n)))
+        dec, out = oracle.ldpc_bp_decode(g["s%02d_llr" % c].copy(), {"n_vnodes": int(n), "parity_check_matrix": H}, "SPA",
+                                         int(iters))
+        assert np.array_equal(dec, g["s%02d_dec" % c]), rel
+        assert np.allclose(out, g["s%02d_out" % c], rtol=1e-9, atol=1e-9), rel
