@@ -117,6 +117,64 @@ class LinkModel:
         return BERs
 
 
+    def _one_transmission(self, msg, receive_size, full_args_decoder):
+        y = self.channel.propagate(self.modulate(msg))
+        nv = self.channel.noise_std ** 2
+        if np.ndim(y) > 1:
+            received = np.empty(int(math.ceil(len(msg) / float(self.rate))))
+            for j in range(len(y)):
+                received[receive_size * j:receive_size * (j + 1)] = \
+                    self.receive(y[j], self.channel.channel_gains[j], self.constellation, nv)
+        else:
+            received = self.receive(y, self.channel.channel_gains, self.constellation, nv)
+        if full_args_decoder:
+            return self.decoder(y, self.channel.channel_gains, self.constellation, nv, received,
+                                self.channel.nb_tx * self.num_bits_symbol)
+        return self.decoder(received)
+
+    def link_performance_full_metrics(self, SNRs, tx_max, err_min, send_chunk=None, code_rate=1,
+                                      number_chunks_per_send=1, stop_on_surpass_error=True):
+        """Per-transmission metrics (links.py:155-267): returns (BERs, BEs, CEs, NCs) and caches them on
+        `full_simulation_results`.  A transmission carries `number_chunks_per_send` chunks encoded and decoded as ONE
+        stream (:229-230, :250); errors are then counted per chunk (:252-256)."""
+        BERs = np.zeros_like(SNRs, dtype=float)
+        BEs = np.zeros((len(SNRs), tx_max), dtype=int)
+        CEs = np.zeros((len(SNRs), tx_max), dtype=int)
+        NCs = np.zeros((len(SNRs), tx_max), dtype=int)
+        if send_chunk is None:
+            send_chunk = err_min
+        if type(code_rate) is float:
+            code_rate = Fraction(code_rate).limit_denominator(100)
+        self.rate = code_rate
+        divider = (Fraction(1, self.num_bits_symbol * self.channel.nb_tx) * 1 / code_rate).denominator
+        send_chunk = max(divider, send_chunk // divider * divider)
+        receive_size = self.channel.nb_tx * self.num_bits_symbol
+        full_args_decoder = len(getfullargspec(self.decoder).args) > 1
+        for i, snr in enumerate(SNRs):
+            self.channel.set_SNR_dB(snr, float(code_rate), self.Es)
+            sent = 0
+            bit_err = np.zeros(tx_max, dtype=int)
+            chunk_count = np.zeros(tx_max, dtype=int)
+            for tx in range(tx_max):
+                if stop_on_surpass_error and bit_err.sum() > err_min:
+                    break
+                msg = np.random.choice((0, 1), send_chunk * number_chunks_per_send)
+                decoded = np.asarray(self._one_transmission(msg, receive_size, full_args_decoder))
+                for c in range(number_chunks_per_send):
+                    sl = slice(send_chunk * c, send_chunk * (c + 1))
+                    bit_err[tx] += np.bitwise_xor(msg[sl], decoded[sl].astype(int)).sum()
+                chunk_count[tx] += number_chunks_per_send
+                sent += 1
+            BERs[i] = bit_err.sum() / (sent * send_chunk)
+            BEs[i] = bit_err
+            CEs[i] = np.where(bit_err > 0, 1, 0)
+            NCs[i] = chunk_count
+            if BEs[i].sum() < err_min:
+                break
+        self.full_simulation_results = BERs, BEs, CEs, NCs
+        return BERs, BEs, CEs, NCs
+
+
 def _ff_taps(trellis):
     """Generator taps (delay 0 = current input) of a k=1 feed-forward shift-register trellis, or None."""
     if trellis.k != 1:

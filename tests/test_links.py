@@ -95,3 +95,26 @@ def test_dropin_linkmodel_with_gpu_receiver_and_decoder():
     model = LinkModel(modulate, ch, receiver_hard, modem.num_bits_symbol, modem.constellation, modem.Es, decoder_hard, 0.5)
     ber = model.link_performance(np.array([5.0]) + 10 * math.log10(2), 40000, 200, 1000, 0.5)[0]
     assert 1e-4 < ber < 4e-3, ber                # commpy/channelcoding/README.md:159-160 quotes 7.8e-4 (hard, 5 dB)
+
+
+def test_wifi80211_tables_match_reference():
+    from commpy_b200.wifi80211 import Wifi80211
+    assert [Wifi80211(m)._get_coding() for m in range(10)] == [(1, 2), (1, 2), (3, 4), (1, 2), (3, 4), (2, 3), (3, 4),
+                                                              (5, 6), (3, 4), (5, 6)]
+    assert [Wifi80211(m).get_modem().m for m in range(10)] == [2, 4, 4, 16, 16, 64, 64, 64, 256, 256]
+    assert Wifi80211._get_puncture_matrix(3, 4) == [1, 1, 1, 0, 0, 1] and Wifi80211._get_puncture_matrix(1, 2) is None
+    tr = Wifi80211._get_trellis()            # decimal (133,171) quirk: taps (5, 43)
+    assert np.array_equal(tr.output_table, helpers.k7_wifi_quirk().output_table)
+
+
+@pytest.mark.gpu
+def test_wifi80211_link_performance_runs_on_gpu_path():
+    """Wifi80211(mcs).link_performance end to end (punctured 3/4 and unpunctured), BER falls with SNR."""
+    from commpy_b200.wifi80211 import Wifi80211
+    np.random.seed(11)
+    for mcs, snrs in ((1, np.array([4.0, 12.0])), (4, np.array([10.0, 22.0]))):
+        w = Wifi80211(mcs)
+        ch = AwgnSisoChannel(rng=np.random.RandomState(12))
+        BERs, BEs, CEs, NCs = w.link_performance(ch, snrs, 12, 1, 600, stop_on_surpass_error=False)
+        assert BERs.shape == (2,) and BEs.shape == (2, 12) and NCs.sum() == 24
+        assert BERs[0] > BERs[1] and BERs[1] < 0.05, (mcs, BERs)
