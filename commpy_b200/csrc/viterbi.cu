@@ -84,7 +84,7 @@ static bool code_matches(const cpbTrellis &t)
 // ------------------------------------------------------------------------------------------------
 namespace fast {
 
-constexpr int TBB = 16;            // windows per traceback block
+constexpr int TBB = 24;            // windows per traceback block
 constexpr int QBITS = 19;          // |quantised LLR| <= 2^19
 constexpr int QMAX = 1 << QBITS;
 constexpr int BD = 32;             // one warp per CTA: every synchronisation below is a __syncwarp()

@@ -3,7 +3,7 @@ survivor ring of D+9 steps, 16-window block traceback with per-window fallback, 
 Used on CPU to check the kernel's ALGORITHM against the oracle before spending GPU time."""
 import numpy as np
 
-TBB = 16
+TBB = 24
 
 
 def out_sym(M, G0, G1, s, u):
