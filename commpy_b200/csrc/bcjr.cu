@@ -351,6 +351,183 @@ __global__ void __launch_bounds__(128) map_tpf_kernel(const Params p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Checkpointed variant of the kernel above (the one that runs when N % 4 == 0): beta is written to HBM only every
+// CK-th step.  The forward sweep then works segment by segment: reload the CK steps of inputs into shared memory,
+// recompute the segment's beta backwards from its checkpoint (same operations in the same order as the first
+// sweep, so the same values), then run alpha / the a-posteriori LLRs forwards.  This trades +1 beta recursion per
+// step for 8x less beta traffic: the plain kernel moved 4.7 GB per pass for a batch of 8192 x 6144 (3.2 GB of it
+// beta), i.e. it was HBM bound on non-algorithmic bytes (profiles/r01_other_kernels_ncu.md).
+// Shared memory per thread: CK*(S+3) floats, thread-private columns [slot][thread] (conflict free).
+// ------------------------------------------------------------------------------------------------
+constexpr int CK = 8;
+
+template <class T>
+__global__ void __launch_bounds__(128) map_ckpt_kernel(const Params p)
+{
+    constexpr int S = T::S;
+    constexpr int G = 4;
+    extern __shared__ float smem_f[];
+    const int tid = threadIdx.x, bd = blockDim.x;
+    float *sb = smem_f;                         // [CK][S][bd]   beta of the current segment
+    float *si = smem_f + CK * S * bd;           // [CK][3][bd]   sys, par, La of the current segment
+    const int64_t g = (int64_t)blockIdx.x * bd + tid;
+    if (g >= p.NT) return;
+    const int w = (int)(g / p.bp);
+    const int64_t f = g - (int64_t)w * p.bp;
+    if (f >= p.batch) return;
+    const int N = p.N;
+    const int lo = w * p.win, hi = min(N, lo + p.win);
+    const float *fs = p.sys + f * N, *fp = p.par + f * N, *fl = p.La + f * N;
+    float *ck = p.beta + g;                     // checkpoints: [(j*S + s) * NT + thread], j = segment index
+
+    auto branch = [&](float ys, float yp, float (&gm)[4]) {
+        const float a = ys * p.c, b = yp * p.c;
+        gm[0] = -a - b; gm[1] = b - a; gm[2] = a - b; gm[3] = a + b;
+    };
+    auto beta_step = [&](float (&B)[S], float ys, float yp, float la_raw, int t) {     // beta_t -> beta_{t-1}
+        float gm[4];
+        branch(ys, yp, gm);
+        const float la = la_raw * LOG2E;
+        float Bn[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            Bn[s] = maxstar2(B[T::ns(s, 0)] + gm[T::out(s, 0)], B[T::ns(s, 1)] + gm[T::out(s, 1)] + la);
+        if ((t & 3) == 1) {
+            float m = Bn[0];
+#pragma unroll
+            for (int s = 1; s < S; ++s) m = fmaxf(m, Bn[s]);
+#pragma unroll
+            for (int s = 0; s < S; ++s) Bn[s] -= m;
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) B[s] = Bn[s];
+    };
+    auto ld4 = [&](const float *q, int e0, float (&v)[G]) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(q + e0));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    };
+
+    // ---- backward sweep, checkpoint beta at the end of every segment
+    {
+        float B[S];
+        const int tb = min(N, hi + WARM);
+#pragma unroll
+        for (int s = 0; s < S; ++s) B[s] = 0.0f;
+        float ns_[G], np_[G], nl_[G];
+        ld4(fs, tb - G, ns_); ld4(fp, tb - G, np_); ld4(fl, tb - G, nl_);
+        for (int e1 = tb; e1 > lo; e1 -= G) {
+            float vs[G], vp[G], vl[G];
+#pragma unroll
+            for (int i = 0; i < G; ++i) { vs[i] = ns_[i]; vp[i] = np_[i]; vl[i] = nl_[i]; }
+            if (e1 - G > lo) { ld4(fs, e1 - 2 * G, ns_); ld4(fp, e1 - 2 * G, np_); ld4(fl, e1 - 2 * G, nl_); }
+#pragma unroll
+            for (int i = G - 1; i >= 0; --i) {
+                const int t = e1 - (G - 1 - i);
+                if (t <= hi && (((t - lo) % CK) == 0 || t == hi)) {
+                    const int j = (t - lo + CK - 1) / CK - 1;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) ck[((int64_t)j * S + s) * p.NT] = B[s];
+                }
+                beta_step(B, vs[i], vp[i], vl[i], t);
+            }
+        }
+    }
+    // ---- forward sweep
+    float A[S];
+    const int ta = max(0, lo - WARM);
+#pragma unroll
+    for (int s = 0; s < S; ++s) A[s] = (ta == 0 && s != 0) ? NEGM : 0.0f;
+    auto alpha_step = [&](float ys, float yp, float la_raw, int t, const float *bt, bool emit, float &Lout) {
+        float gm[4];
+        branch(ys, yp, gm);
+        const float la = la_raw * LOG2E;
+        float tx[2 * S];
+#pragma unroll
+        for (int e = 0; e < 2 * S; ++e) tx[e] = A[e >> 1] + gm[T::out(e >> 1, e & 1)];
+        if (emit) {
+            float x0[S], x1[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                x0[s] = tx[2 * s] + bt[T::ns(s, 0) * bd];
+                x1[s] = tx[2 * s + 1] + bt[T::ns(s, 1) * bd];
+            }
+            float m0 = x0[0], m1 = x1[0];
+#pragma unroll
+            for (int s = 1; s < S; ++s) { m0 = fmaxf(m0, x0[s]); m1 = fmaxf(m1, x1[s]); }
+            float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+            for (int s = 0; s < S; ++s) { s0 += ex2(x0[s] - m0); s1 += ex2(x1[s] - m1); }
+            Lout = la_raw + LN2 * ((m1 + lg2(s1)) - (m0 + lg2(s0)));
+        }
+        float An[S];
+#pragma unroll
+        for (int n = 0; n < S; ++n) {
+            const int ea = T::pred(n, 0), eb = T::pred(n, 1);
+            An[n] = maxstar2(tx[ea] + ((ea & 1) ? la : 0.0f), tx[eb] + ((eb & 1) ? la : 0.0f));
+        }
+        if ((t & 3) == 0) {
+            float m = An[0];
+#pragma unroll
+            for (int s = 1; s < S; ++s) m = fmaxf(m, An[s]);
+#pragma unroll
+            for (int s = 0; s < S; ++s) An[s] = fmaxf(An[s] - m, NEGM);
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) A[s] = An[s];
+    };
+    // warm-up (no LLRs, no beta)
+    for (int e0 = ta; e0 < lo; e0 += G) {
+        float vs[G], vp[G], vl[G];
+        ld4(fs, e0, vs); ld4(fp, e0, vp); ld4(fl, e0, vl);
+        float dummy;
+#pragma unroll
+        for (int i = 0; i < G; ++i) alpha_step(vs[i], vp[i], vl[i], e0 + 1 + i, nullptr, false, dummy);
+    }
+    // segments
+    for (int s0 = lo, j = 0; s0 < hi; s0 += CK, ++j) {
+        const int ns = min(CK, hi - s0);                      // a multiple of 4
+        // inputs of the segment -> shared memory
+        for (int q = 0; q < ns; q += G) {
+            float vs[G], vp[G], vl[G];
+            ld4(fs, s0 + q, vs); ld4(fp, s0 + q, vp); ld4(fl, s0 + q, vl);
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                si[((q + i) * 3 + 0) * bd + tid] = vs[i];
+                si[((q + i) * 3 + 1) * bd + tid] = vp[i];
+                si[((q + i) * 3 + 2) * bd + tid] = vl[i];
+            }
+        }
+        // beta of the segment, backwards from its checkpoint (beta at step s0+ns)
+        float B[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) B[s] = ck[((int64_t)j * S + s) * p.NT];
+        for (int i = ns - 1; i >= 0; --i) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) sb[(i * S + s) * bd + tid] = B[s];          // beta_{s0+1+i}
+            beta_step(B, si[(i * 3 + 0) * bd + tid], si[(i * 3 + 1) * bd + tid], si[(i * 3 + 2) * bd + tid], s0 + 1 + i);
+        }
+        // alpha / LLR forwards
+        for (int q = 0; q < ns; q += G) {
+            float Lv[G];
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const int k = q + i;
+                alpha_step(si[(k * 3 + 0) * bd + tid], si[(k * 3 + 1) * bd + tid], si[(k * 3 + 2) * bd + tid], s0 + 1 + k,
+                           sb + (k * S) * bd + tid, true, Lv[i]);
+            }
+            const int e0 = s0 + q;
+            *reinterpret_cast<float4 *>(p.L_out + f * N + e0) = make_float4(Lv[0], Lv[1], Lv[2], Lv[3]);
+            if (p.bits_out) {
+                uchar4 b;
+                b.x = (p.mode == 1 && Lv[0] > 0.0f); b.y = (p.mode == 1 && Lv[1] > 0.0f);
+                b.z = (p.mode == 1 && Lv[2] > 0.0f); b.w = (p.mode == 1 && Lv[3] > 0.0f);
+                *reinterpret_cast<uchar4 *>(p.bits_out + f * N + e0) = b;
+            }
+        }
+    }
+}
+
 // compile-time trellises this kernel is instantiated for (packed from commpy_b200's Trellis tables)
 using RscK4 = CT<8, 0xedfc96369120ull, 0xc99cc99cu>;         // Trellis([3], [[1, 0o15]], [[0o13]], 'rsc')  (config C3)
 using RscK4Legacy = CT<8, 0xedf5b2a4d120ull, 0xcc9999ccu>;   // Trellis([3], [[1, 0o15]], 0o13, 'rsc')
@@ -374,7 +551,11 @@ template <class T>
 static int launch(const Params &p, bool vec, cudaStream_t st)
 {
     const unsigned grid = (unsigned)ceil_div(p.NT, 128);
-    if (vec) map_tpf_kernel<T, 4><<<grid, 128, 0, st>>>(p);
+    if (vec && (p.win % CK) == 0) {
+        const size_t smem = sizeof(float) * CK * (T::S + 3) * 128;
+        CPB_CUDA(cudaFuncSetAttribute(map_ckpt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        map_ckpt_kernel<T><<<grid, 128, smem, st>>>(p);
+    } else if (vec) map_tpf_kernel<T, 4><<<grid, 128, 0, st>>>(p);
     else map_tpf_kernel<T, 1><<<grid, 128, 0, st>>>(p);
     CPB_LAUNCH_CHECK();
     return CPB_OK;
