@@ -528,6 +528,182 @@ __global__ void __launch_bounds__(128) map_ckpt_kernel(const Params p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Probability-domain variant (what actually runs for N % 4 == 0): the log-domain kernels above spend 66 MUFU
+// operations per trellis step (ex2 + lg2 per max*) and are bound by the 16-lane XU pipe.  The reference itself
+// works with probabilities renormalised every step (turbo.py:106-111, :155); doing the same in fp32 needs only
+// multiplies and adds for the recursions:
+//   branch weight of output symbol (cs, cp), relative to the best symbol of the step (all weights <= 1, no
+//   overflow):  w = [cs opposes ys ? 2^(-2|a|) : 1] * [cp opposes yp ? 2^(-2|b|) : 1],  a = ys log2e/s^2, b = yp log2e/s^2
+//   prior odds P(1)/P(0) = e^La, also relative to the larger:  (p0, p1) = La > 0 ? (2^(-La log2e), 1) : (1, 2^(La log2e))
+//   beta_{t-1}(s) = sum_u p_u w(s,u) beta_t(ns(s,u)),  alpha_t(ns) += p_u w(s,u) alpha_{t-1}(s),  both rescaled to sum 1
+//   L_t = La + ln( sum_s alpha w(s,1) beta / sum_s alpha w(s,0) beta )
+// i.e. 2 + 1 ex2, 3 reciprocals and 2 lg2 per step instead of 66 MUFU ops.  |a|, |b|, |La log2e| are clamped to 60
+// so nothing reaches the fp32 exponent limits; the clamp only acts where |LLR| > ~80.  Beta is checkpointed every
+// CK steps and recomputed per segment in shared memory exactly like map_ckpt_kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+template <class T>
+__global__ void __launch_bounds__(128) map_lin_kernel(const Params p)
+{
+    constexpr int S = T::S;
+    constexpr int G = 4;
+    extern __shared__ float smem_f[];
+    const int tid = threadIdx.x, bd = blockDim.x;
+    float *sb = smem_f;                         // [CK][S][bd]
+    float *si = smem_f + CK * S * bd;           // [CK][3][bd]
+    const int64_t g = (int64_t)blockIdx.x * bd + tid;
+    if (g >= p.NT) return;
+    const int w = (int)(g / p.bp);
+    const int64_t f = g - (int64_t)w * p.bp;
+    if (f >= p.batch) return;
+    const int N = p.N;
+    const int lo = w * p.win, hi = min(N, lo + p.win);
+    const float *fs = p.sys + f * N, *fp = p.par + f * N, *fl = p.La + f * N;
+    float *ck = p.beta + g;
+
+    // weights of the four output symbols (index o = cs<<1 | cp with cs/cp = 1 for +1) and the two prior factors
+    auto weights = [&](float ys, float yp, float la_raw, float (&wt)[4], float &p0, float &p1) {
+        const float a = fminf(fmaxf(ys * p.c, -60.0f), 60.0f), b = fminf(fmaxf(yp * p.c, -60.0f), 60.0f);
+        const float ea = ex2(-2.0f * fabsf(a)), eb = ex2(-2.0f * fabsf(b));
+        const float s1 = (a >= 0.0f) ? 1.0f : ea, s0 = (a >= 0.0f) ? ea : 1.0f;      // systematic bit +1 / -1
+        const float q1 = (b >= 0.0f) ? 1.0f : eb, q0 = (b >= 0.0f) ? eb : 1.0f;      // parity bit +1 / -1
+        wt[0] = s0 * q0; wt[1] = s0 * q1; wt[2] = s1 * q0; wt[3] = s1 * q1;
+        const float l = fminf(fmaxf(la_raw * LOG2E, -60.0f), 60.0f);
+        const float el = ex2(-fabsf(l));
+        p0 = (l > 0.0f) ? el : 1.0f;
+        p1 = (l > 0.0f) ? 1.0f : el;
+    };
+    auto normalise = [&](float (&v)[S]) {
+        float sum = v[0];
+#pragma unroll
+        for (int s = 1; s < S; ++s) sum += v[s];
+        const float r = rcp(fmaxf(sum, 1.0e-37f));
+#pragma unroll
+        for (int s = 0; s < S; ++s) v[s] *= r;
+    };
+    auto beta_step = [&](float (&B)[S], float ys, float yp, float la_raw) {           // beta_t -> beta_{t-1}
+        float wt[4], p0, p1;
+        weights(ys, yp, la_raw, wt, p0, p1);
+        float w0[4], w1[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) { w0[o] = wt[o] * p0; w1[o] = wt[o] * p1; }
+        float Bn[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            Bn[s] = w0[T::out(s, 0)] * B[T::ns(s, 0)] + w1[T::out(s, 1)] * B[T::ns(s, 1)];      // turbo.py:106-108
+        normalise(Bn);                                                                          // :110-111
+#pragma unroll
+        for (int s = 0; s < S; ++s) B[s] = Bn[s];
+    };
+    auto ld4 = [&](const float *q, int e0, float (&v)[G]) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(q + e0));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    };
+
+    // ---- backward sweep with checkpoints
+    {
+        float B[S];
+        const int tb = min(N, hi + WARM);
+#pragma unroll
+        for (int s = 0; s < S; ++s) B[s] = 1.0f / S;                      // beta_N = 1 for all states (:225-226), scale free
+        float ns_[G], np_[G], nl_[G];
+        ld4(fs, tb - G, ns_); ld4(fp, tb - G, np_); ld4(fl, tb - G, nl_);
+        for (int e1 = tb; e1 > lo; e1 -= G) {
+            float vs[G], vp[G], vl[G];
+#pragma unroll
+            for (int i = 0; i < G; ++i) { vs[i] = ns_[i]; vp[i] = np_[i]; vl[i] = nl_[i]; }
+            if (e1 - G > lo) { ld4(fs, e1 - 2 * G, ns_); ld4(fp, e1 - 2 * G, np_); ld4(fl, e1 - 2 * G, nl_); }
+#pragma unroll
+            for (int i = G - 1; i >= 0; --i) {
+                const int t = e1 - (G - 1 - i);
+                if (t <= hi && (((t - lo) % CK) == 0 || t == hi)) {
+                    const int j = (t - lo + CK - 1) / CK - 1;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) ck[((int64_t)j * S + s) * p.NT] = B[s];
+                }
+                beta_step(B, vs[i], vp[i], vl[i]);
+            }
+        }
+    }
+    // ---- forward sweep
+    float A[S];
+    const int ta = max(0, lo - WARM);
+#pragma unroll
+    for (int s = 0; s < S; ++s) A[s] = (ta == 0) ? ((s == 0) ? 1.0f : 0.0f) : (1.0f / S);    // alpha_0 = delta(s,0), :220-221
+    auto alpha_step = [&](float ys, float yp, float la_raw, const float *bt, bool emit, float &Lout) {
+        float wt[4], p0, p1;
+        weights(ys, yp, la_raw, wt, p0, p1);
+        float tx[2 * S];
+#pragma unroll
+        for (int e = 0; e < 2 * S; ++e) tx[e] = A[e >> 1] * wt[T::out(e >> 1, e & 1)];
+        if (emit) {
+            float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {                       // the a-posteriori sums leave the prior out (:141-143)
+                a0 += tx[2 * s] * bt[T::ns(s, 0) * bd];
+                a1 += tx[2 * s + 1] * bt[T::ns(s, 1) * bd];
+            }
+            Lout = la_raw + LN2 * (lg2(fmaxf(a1, 1.0e-37f)) - lg2(fmaxf(a0, 1.0e-37f)));       // :145
+        }
+        float An[S];
+#pragma unroll
+        for (int n = 0; n < S; ++n) {
+            const int ea = T::pred(n, 0), eb = T::pred(n, 1);
+            An[n] = tx[ea] * ((ea & 1) ? p1 : p0) + tx[eb] * ((eb & 1) ? p1 : p0);             // :136-138
+        }
+        normalise(An);                                                                          // :155
+#pragma unroll
+        for (int s = 0; s < S; ++s) A[s] = An[s];
+    };
+    for (int e0 = ta; e0 < lo; e0 += G) {                       // warm-up (no LLRs, no beta)
+        float vs[G], vp[G], vl[G];
+        ld4(fs, e0, vs); ld4(fp, e0, vp); ld4(fl, e0, vl);
+        float dummy;
+#pragma unroll
+        for (int i = 0; i < G; ++i) alpha_step(vs[i], vp[i], vl[i], nullptr, false, dummy);
+    }
+    for (int s0 = lo, j = 0; s0 < hi; s0 += CK, ++j) {
+        const int ns = min(CK, hi - s0);                        // a multiple of 4
+        for (int q = 0; q < ns; q += G) {
+            float vs[G], vp[G], vl[G];
+            ld4(fs, s0 + q, vs); ld4(fp, s0 + q, vp); ld4(fl, s0 + q, vl);
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                si[((q + i) * 3 + 0) * bd + tid] = vs[i];
+                si[((q + i) * 3 + 1) * bd + tid] = vp[i];
+                si[((q + i) * 3 + 2) * bd + tid] = vl[i];
+            }
+        }
+        float B[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) B[s] = ck[((int64_t)j * S + s) * p.NT];
+        for (int i = ns - 1; i >= 0; --i) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) sb[(i * S + s) * bd + tid] = B[s];          // beta_{s0+1+i}
+            beta_step(B, si[(i * 3 + 0) * bd + tid], si[(i * 3 + 1) * bd + tid], si[(i * 3 + 2) * bd + tid]);
+        }
+        for (int q = 0; q < ns; q += G) {
+            float Lv[G];
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const int k = q + i;
+                alpha_step(si[(k * 3 + 0) * bd + tid], si[(k * 3 + 1) * bd + tid], si[(k * 3 + 2) * bd + tid],
+                           sb + (k * S) * bd + tid, true, Lv[i]);
+            }
+            const int e0 = s0 + q;
+            *reinterpret_cast<float4 *>(p.L_out + f * N + e0) = make_float4(Lv[0], Lv[1], Lv[2], Lv[3]);
+            if (p.bits_out) {
+                uchar4 b;
+                b.x = (p.mode == 1 && Lv[0] > 0.0f); b.y = (p.mode == 1 && Lv[1] > 0.0f);
+                b.z = (p.mode == 1 && Lv[2] > 0.0f); b.w = (p.mode == 1 && Lv[3] > 0.0f);
+                *reinterpret_cast<uchar4 *>(p.bits_out + f * N + e0) = b;
+            }
+        }
+    }
+}
+
 // compile-time trellises this kernel is instantiated for (packed from commpy_b200's Trellis tables)
 using RscK4 = CT<8, 0xedfc96369120ull, 0xc99cc99cu>;         // Trellis([3], [[1, 0o15]], [[0o13]], 'rsc')  (config C3)
 using RscK4Legacy = CT<8, 0xedf5b2a4d120ull, 0xcc9999ccu>;   // Trellis([3], [[1, 0o15]], 0o13, 'rsc')
@@ -553,8 +729,13 @@ static int launch(const Params &p, bool vec, cudaStream_t st)
     const unsigned grid = (unsigned)ceil_div(p.NT, 128);
     if (vec && (p.win % CK) == 0) {
         const size_t smem = sizeof(float) * CK * (T::S + 3) * 128;
+#ifdef CPB_BCJR_LOGDOMAIN
         CPB_CUDA(cudaFuncSetAttribute(map_ckpt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         map_ckpt_kernel<T><<<grid, 128, smem, st>>>(p);
+#else
+        CPB_CUDA(cudaFuncSetAttribute(map_lin_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        map_lin_kernel<T><<<grid, 128, smem, st>>>(p);
+#endif
     } else if (vec) map_tpf_kernel<T, 4><<<grid, 128, 0, st>>>(p);
     else map_tpf_kernel<T, 1><<<grid, 128, 0, st>>>(p);
     CPB_LAUNCH_CHECK();
@@ -589,6 +770,39 @@ __global__ void __launch_bounds__(256) scatter_sub_kernel(const float *__restric
         const int i = (int)(g - f * N);
         out[f * N + __ldg(&perm[i])] = a[g] - b[g];
     }
+}
+
+// Row-staged forms of the three permutation kernels (one CTA per frame, the frame's row lives in shared memory):
+// the global side is fully coalesced and the random access of the interleaver happens in shared memory.
+// (The element-wise forms above issue one 32-byte sector request per 4-byte element: 0.35 ms per call at C3.)
+__global__ void __launch_bounds__(256) row_gather_sub_kernel(const float *__restrict__ a, const float *__restrict__ b,
+                                                             const int32_t *__restrict__ perm, int N, float *__restrict__ out)
+{
+    extern __shared__ float row[];
+    const int64_t base = (int64_t)blockIdx.x * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) row[i] = a[base + i] - (b ? b[base + i] : 0.0f);
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) out[base + i] = row[__ldg(&perm[i])];
+}
+
+__global__ void __launch_bounds__(256) row_scatter_sub_kernel(const float *__restrict__ a, const float *__restrict__ b,
+                                                              const int32_t *__restrict__ perm, int N, float *__restrict__ out)
+{
+    extern __shared__ float row[];
+    const int64_t base = (int64_t)blockIdx.x * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) row[__ldg(&perm[i])] = a[base + i] - b[base + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) out[base + i] = row[i];
+}
+
+__global__ void __launch_bounds__(256) row_scatter_bits_kernel(const uint8_t *__restrict__ a, const int32_t *__restrict__ perm,
+                                                               int N, uint8_t *__restrict__ out)
+{
+    extern __shared__ uint8_t brow[];
+    const int64_t base = (int64_t)blockIdx.x * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) brow[__ldg(&perm[i])] = a[base + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) out[base + i] = brow[i];
 }
 
 __global__ void __launch_bounds__(256) scatter_bits_kernel(const uint8_t *__restrict__ a, const int32_t *__restrict__ perm,
@@ -726,18 +940,29 @@ int cpb_turbo_decode(const cpbTrellis *t, const float *sys_dev, const float *par
         else e = cudaMemsetAsync(La1, 0, tot * sizeof(float), st);                         // turbo.py:304-307
         if (e == cudaSuccess) e = cudaMemsetAsync(dec, 0, tot, st);
         if (e != cudaSuccess) { rc = record_cuda_error(e, "turbo init", __FILE__, __LINE__); break; }
-        bcjr::gather_sub_kernel<<<eg, 256, 0, st>>>(sy, nullptr, perm_dev, nb, (int)N, sys_i);          // :310
+        const bool rows = (size_t)N * sizeof(float) <= 96 * 1024;
+        const size_t rsm = (size_t)N * sizeof(float);
+        if (rows) {
+            cudaFuncSetAttribute(bcjr::row_gather_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
+            cudaFuncSetAttribute(bcjr::row_scatter_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
+            cudaFuncSetAttribute(bcjr::row_scatter_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)N);
+        }
+        if (rows) bcjr::row_gather_sub_kernel<<<(unsigned)nb, 256, rsm, st>>>(sy, nullptr, perm_dev, (int)N, sys_i);
+        else bcjr::gather_sub_kernel<<<eg, 256, 0, st>>>(sy, nullptr, perm_dev, nb, (int)N, sys_i);          // :310
         for (int it = 0; it < n_iter && rc == CPB_OK; ++it) {
             rc = bcjr::launch_map(t, S, sy, p1, La1, nb, (int)N, noise_variance, 0, beta, L1, nullptr, st);   // :315
             if (rc) break;
-            bcjr::gather_sub_kernel<<<eg, 256, 0, st>>>(L1, La1, perm_dev, nb, (int)N, La2);            // :318-319
+            if (rows) bcjr::row_gather_sub_kernel<<<(unsigned)nb, 256, rsm, st>>>(L1, La1, perm_dev, (int)N, La2);
+            else bcjr::gather_sub_kernel<<<eg, 256, 0, st>>>(L1, La1, perm_dev, nb, (int)N, La2);            // :318-319
             const int mode = (it == n_iter - 1) ? 1 : 0;                                                // :320-323
             rc = bcjr::launch_map(t, S, sys_i, p2, La2, nb, (int)N, noise_variance, mode, beta, L2, dec, st);  // :326
             if (rc) break;
-            bcjr::scatter_sub_kernel<<<eg, 256, 0, st>>>(L2, La2, perm_dev, nb, (int)N, La1);           // :328-329
+            if (rows) bcjr::row_scatter_sub_kernel<<<(unsigned)nb, 256, rsm, st>>>(L2, La2, perm_dev, (int)N, La1);
+            else bcjr::scatter_sub_kernel<<<eg, 256, 0, st>>>(L2, La2, perm_dev, nb, (int)N, La1);           // :328-329
         }
         if (rc) break;
-        bcjr::scatter_bits_kernel<<<eg, 256, 0, st>>>(dec, perm_dev, nb, (int)N, bits_out_dev + f0 * N); // :331
+        if (rows) bcjr::row_scatter_bits_kernel<<<(unsigned)nb, 256, (size_t)N, st>>>(dec, perm_dev, (int)N, bits_out_dev + f0 * N);
+        else bcjr::scatter_bits_kernel<<<eg, 256, 0, st>>>(dec, perm_dev, nb, (int)N, bits_out_dev + f0 * N); // :331
         e = cudaGetLastError();
         if (e != cudaSuccess) rc = record_cuda_error(e, "turbo kernels", __FILE__, __LINE__);
     }
