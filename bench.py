@@ -394,8 +394,6 @@ def run_extras(torch):
     for name in ("viterbi_k7_n1024_soft", "viterbi_k7_n4096_soft_c2"):
         try:
             wl = WORKLOADS[name]()
-            if name.endswith("c2"):
-                wl.batch = 16384            # a quarter of C2's batch keeps the default run short; rate is per frame
             wl.make(torch, seed=7, nbuf=2)
             ms = timeit(lambda: wl.decode(0), reps=5, warm=2)
             out[name] = {"value": wl.batch / ms * 1e3, "unit": "codewords/s", "ms": ms, "frames": wl.batch,
@@ -475,7 +473,7 @@ def run_extras(torch):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
