@@ -143,6 +143,29 @@ DEFAULT_WORKLOAD = "viterbi_k7_n1024_hard"
 
 
 # ------------------------------------------------------------------------------------------------ helpers
+def usable_cores():
+    """host threads this process may really use: CPU affinity, capped by the cgroup CPU quota when there is one"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -233,7 +256,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     wl = WORKLOADS[args.workload]()
-    threads = os.cpu_count() or 1
+    threads = usable_cores()
     per_step = []
     frames_step = None
     for s in range(args.warmup + args.steps):
@@ -361,7 +384,7 @@ def run_b200(args):
     }
     if n_gpus == 1:
         line["parity"] = wl.parity(torch)
-        threads = os.cpu_count() or 1
+        threads = usable_cores()
         rate, frames, dt = timed_cpu(wl, threads, target_s=12.0)
         line["cpu_baseline"] = {"value": rate, "unit": "codewords/s", "cores": threads, "kind": "port",
                                 "sample": "%d frames of the same recipe in %.1f s: oracle/commpy_oracle.c (fp64 restatement "

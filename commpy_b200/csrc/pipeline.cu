@@ -62,9 +62,9 @@ extern "C" int cpb_viterbi_decode_host(const cpbTrellis *t, const void *coded_ho
     int rc = cpb_viterbi_sizes(t, n_in, &L, &T);
     if (rc) return rc;
     const size_t esz = (in_dtype == CPB_U8) ? 1 : 4;
-    // chunks of ~1/6 of the batch (at least 8192 frames, a multiple of 2048): enough pieces for the three
+    // chunks of ~1/4 of the batch (at least 8192 frames, a multiple of 2048): enough pieces for the three
     // engines to overlap, large enough to fill the GPU
-    int64_t chunk = ceil_div(ceil_div(batch, 6), 2048) * 2048;
+    int64_t chunk = ceil_div(ceil_div(batch, 4), 2048) * 2048;
     chunk = std::max<int64_t>(chunk, 8192);
     chunk = std::min<int64_t>(chunk, batch);
     int dev = 0;
