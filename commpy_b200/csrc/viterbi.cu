@@ -20,6 +20,7 @@
 // the long path does not pass through that window's own best state, which reproduces the reference's
 // per-step traceback bit for bit.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 #include <vector>
 
@@ -820,6 +821,10 @@ static int resolve_depth(const cpbTrellis *t, int64_t L, int tb_depth)
 static bool use_fast(const cpbTrellis *t, int D, int mode, int in_dtype)
 {
     if (t->fast_id == 0) return false;
+    // test hook: CPB_VITERBI_FORCE_GENERIC=1 routes every trellis through the table-driven kernel, so the two
+    // independent implementations can be compared against each other at full size (tests/test_viterbi_gpu.py)
+    const char *force = getenv("CPB_VITERBI_FORCE_GENERIC");
+    if (force && force[0] == '1') return false;
     if (D < t->M + 1 || D > 48) return false;
     if (mode == CPB_VITERBI_HARD) return in_dtype == CPB_U8;
     return in_dtype == CPB_F32;

@@ -90,3 +90,37 @@ def test_reference_roundtrips_inf_llr():
         cont = conv_encode(msg, tr, termination="cont")
         noisy = 10.0 * cont - 5 + rs.randn(len(cont)) * 2
         assert np.array_equal(viterbi_decode(noisy, tr, 15, "soft"), msg)
+
+
+def test_full_size_properties_and_kernel_cross_check():
+    """BASELINE-size checks that need no oracle: (a) noiseless encode -> decode round trip over a full 65,536-frame
+    batch, hard and soft; (b) the register-resident fast kernel and the table-driven generic kernel -- two independent
+    implementations -- agree bit for bit on 8,192 noisy N=1024 frames (hard) and to 1e-4 (soft)."""
+    import os
+    import torch
+    tr = helpers.k7()
+    rs = np.random.RandomState(15)
+    msgs = rs.randint(0, 2, (4096, 1024))
+    coded = helpers.encode_batch(msgs, tr, "cont").astype(np.uint8)
+    big = torch.from_numpy(coded).cuda().repeat(16, 1).contiguous()              # 65,536 frames
+    out = viterbi_decode_batch(big, tr, None, "hard")
+    want = torch.from_numpy(msgs.astype(np.uint8)).cuda().repeat(16, 1)
+    assert torch.equal(out, want)
+    soft = (2.0 * big.float() - 1.0) * 4.0
+    out = viterbi_decode_batch(soft, tr, None, "soft")
+    assert torch.equal(out, want)
+    del big, soft, out, want
+    _, x = helpers.channel_frames(tr, rs, 8192, 1024, "hard", "cont", flip=0.06)
+    xh = torch.from_numpy(x.astype(np.uint8)).cuda()
+    fast = viterbi_decode_batch(xh, tr, None, "hard")
+    _, xs = helpers.channel_frames(tr, rs, 4096, 1024, "soft", "cont", ebn0_db=2.0)
+    xsf = torch.from_numpy(xs.astype(np.float32)).cuda()
+    fast_s = viterbi_decode_batch(xsf, tr, None, "soft")
+    os.environ["CPB_VITERBI_FORCE_GENERIC"] = "1"
+    try:
+        gen = viterbi_decode_batch(xh, tr, None, "hard")
+        gen_s = viterbi_decode_batch(xsf, tr, None, "soft")
+    finally:
+        del os.environ["CPB_VITERBI_FORCE_GENERIC"]
+    assert torch.equal(fast, gen)
+    assert (fast_s != gen_s).float().mean().item() <= 1e-4
