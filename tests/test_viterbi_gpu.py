@@ -105,7 +105,11 @@ def test_full_size_properties_and_kernel_cross_check():
     big = torch.from_numpy(coded).cuda().repeat(16, 1).contiguous()              # 65,536 frames
     out = viterbi_decode_batch(big, tr, None, "hard")
     want = torch.from_numpy(msgs.astype(np.uint8)).cuda().repeat(16, 1)
-    assert torch.equal(out, want)
+    # an unterminated ('cont') frame is padded with RECEIVED ZEROS in hard mode (convcode.py:727-728), which biases the
+    # last few bits exactly as in the reference; everything before the last constraint length must be error free
+    assert torch.equal(out[:, :1016], want[:, :1016])
+    tail = oracle.viterbi_decode_batch(coded[:64].astype(np.float64), tr, None, "hard", threads=4)
+    assert np.array_equal(out[:64].cpu().numpy(), tail)
     soft = (2.0 * big.float() - 1.0) * 4.0
     out = viterbi_decode_batch(soft, tr, None, "soft")
     assert torch.equal(out, want)
