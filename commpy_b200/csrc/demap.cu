@@ -43,6 +43,9 @@ struct SepTables {
 // re-accumulated relative to the group's own nearest point (rare: |LLR| > 69).
 constexpr float TINY = 7.8886e-31f;     // 2^-100
 
+// raw MUFU.EX2 (ex2a() adds range handling for denormal results that the sums below do not need)
+__device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // one axis of a separable constellation: R levels, HB = log2(R) bits; out[h] = LLR of axis bit h (LSB = 0)
 template <int HB>
 __device__ __forceinline__ void axis_llr(float y, const float *__restrict__ lev, float inv_nv_log2e, float (&out)[HB])
@@ -61,7 +64,7 @@ __device__ __forceinline__ void axis_llr(float y, const float *__restrict__ lev,
     for (int h = 0; h < HB; ++h) { num[h] = 0.0f; den[h] = 0.0f; }
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-        const float e = exp2f(dmin - d[i]);
+        const float e = ex2a(dmin - d[i]);
 #pragma unroll
         for (int h = 0; h < HB; ++h) {
             if ((i >> h) & 1) num[h] += e; else den[h] += e;
@@ -80,7 +83,7 @@ __device__ __forceinline__ void axis_llr(float y, const float *__restrict__ lev,
                     if (((i >> h) & 1) == g) dg = fminf(dg, d[i]);
 #pragma unroll
                 for (int i = 0; i < R; ++i)
-                    if (((i >> h) & 1) == g) sg += exp2f(dg - d[i]);
+                    if (((i >> h) & 1) == g) sg += ex2a(dg - d[i]);
                 const float l = (dmin - dg) + __log2f(sg);
                 if (g) l1 = l; else l0 = l;
             }
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(256) demod_soft_general(const float2 *__restri
     for (int b = 0; b < NB; ++b) { num[b] = 0.0f; den[b] = 0.0f; }
     for (int k = 0; k < M; ++k) {
         const float a = v.x - sc[k].x, b2 = v.y - sc[k].y;
-        const float e = exp2f(dmin - (a * a + b2 * b2) * inv_nv_log2e);
+        const float e = ex2a(dmin - (a * a + b2 * b2) * inv_nv_log2e);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             if ((k >> b) & 1) num[b] += e; else den[b] += e;
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(256) demod_soft_general(const float2 *__restri
                 for (int k = 0; k < M; ++k)
                     if (((k >> b) & 1) == g) {
                         const float a = v.x - sc[k].x, b2 = v.y - sc[k].y;
-                        sg += exp2f(dg - (a * a + b2 * b2) * inv_nv_log2e);
+                        sg += ex2a(dg - (a * a + b2 * b2) * inv_nv_log2e);
                     }
                 const float l = (dmin - dg) + __log2f(sg);
                 if (g) l1 = l; else l0 = l;
