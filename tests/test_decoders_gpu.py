@@ -302,3 +302,30 @@ def test_ldpc_spa_matches_reference_golden():
     # fp32 throughput mode: decisions of converged blocks agree
     dec32, _ = ldpc_bp_decode(g["s00_llr"].copy(), _golden_ldpc(0)[1], "SPA", 20, precision="fp32")
     assert (dec32 == g["s00_dec"]).mean() > 0.99
+
+
+def test_edge_cases_other_decoders():
+    import torch
+    # demapper: zero and one symbol
+    q = QAMModem(16)
+    assert q.demodulate(np.zeros(0, complex), "soft", 1.0).shape == (0,)
+    one = q.demodulate(np.array([0.3 - 1.2j]), "soft", 0.7)
+    assert np.allclose(one, oracle.demodulate(q, np.array([0.3 - 1.2j]), "soft", 0.7), rtol=5e-4, atol=5e-4)
+    # LDPC: zero iterations returns the (clipped) channel decisions, single block, batch that is not a multiple of 4
+    g, params, _ = _golden_ldpc(0)
+    llr = g["l00_llr"].copy()
+    dec, out = ldpc_bp_decode(llr.copy(), params, "MSA", 0)
+    assert np.array_equal(dec, np.signbit(llr).astype(np.int8)) and np.array_equal(out, np.clip(llr, -500, 500))
+    rs = np.random.RandomState(29)
+    x = rs.randn(7, 96) * 3
+    want_dec, want_out = oracle.ldpc_bp_decode(x.reshape(-1).copy(), params, "MSA", 15)
+    dec, out = ldpc_bp_decode_batch(x.copy(), params, 15, "fp64")
+    assert np.array_equal(dec.cpu().numpy(), want_dec.T) and np.array_equal(out.cpu().numpy(), want_out.T)
+    # MAP: a single very short frame, and a batch of 3
+    tr = helpers.rsc_k4()
+    for N, batch in ((4, 1), (12, 3)):
+        ys, yp, La = rs.randn(batch, N), rs.randn(batch, N), rs.randn(batch, N)
+        L, bits = map_decode_batch(ys, yp, tr, 0.9, La)
+        for b in range(batch):
+            Lo, bo = oracle.map_decode(ys[b], yp[b], tr, 0.9, La[b])
+            assert np.allclose(L[b].cpu().numpy(), Lo, rtol=1e-4, atol=1e-4)

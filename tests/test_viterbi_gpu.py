@@ -128,3 +128,38 @@ def test_full_size_properties_and_kernel_cross_check():
         del os.environ["CPB_VITERBI_FORCE_GENERIC"]
     assert torch.equal(fast, gen)
     assert (fast_s != gen_s).float().mean().item() <= 1e-4
+
+
+def test_edge_cases_sizes_and_alignment():
+    """Empty batch, single frame, batch sizes that do not fill a warp, odd input lengths (unaligned rows), the shortest
+    frames / depths the reference semantics allow."""
+    import torch
+    tr = helpers.k7()
+    rs = np.random.RandomState(16)
+    # empty batch
+    out = viterbi_decode_batch(np.zeros((0, 2048), np.uint8), tr, None, "hard")
+    assert out.shape == (0, 1024)
+    out = viterbi_decode_batch(torch.zeros((0, 64), dtype=torch.float32, device="cuda"), tr, None, "soft")
+    assert tuple(out.shape) == (0, 32)
+    for mode in ("hard", "soft", "unquantized"):
+        for batch in (1, 31, 33, 65, 129):
+            for nbits, term in ((40, "term"), (41, "cont"), (16, "cont"), (1023, "cont")):
+                _, x = helpers.channel_frames(tr, rs, batch, nbits, mode, term, flip=0.05, ebn0_db=2.0)
+                if nbits == 41:
+                    x = x[:, :-1]                    # odd number of coded values: the last one is ignored (L = int(len/2))
+                want = oracle.viterbi_decode_batch(x, tr, None, mode, threads=4)
+                xin = x.astype(np.uint8) if mode == "hard" else x.astype(np.float32)
+                got = viterbi_decode_batch(xin, tr, None, mode)
+                if mode == "hard":
+                    assert np.array_equal(got, want), (mode, batch, nbits)
+                else:
+                    assert (got == want).mean() >= 0.999, (mode, batch, nbits)
+    # smallest depth (generic kernel: D = 2) and the largest the fast path takes (48), device-resident unaligned view
+    _, x = helpers.channel_frames(tr, rs, 9, 200, "hard", "cont", flip=0.05)
+    for tb in (2, 3, 6, 48, 49, 120):
+        assert np.array_equal(viterbi_decode_batch(x.astype(np.uint8), tr, tb, "hard"),
+                              oracle.viterbi_decode_batch(x, tr, tb, "hard")), tb
+    big = torch.from_numpy(np.concatenate([np.zeros((9, 3)), x], axis=1).astype(np.uint8)).cuda()
+    view = big[:, 3:]                                # non-contiguous view: the wrapper must densify it
+    assert np.array_equal(viterbi_decode_batch(view, tr, None, "hard").cpu().numpy(),
+                          oracle.viterbi_decode_batch(x, tr, None, "hard"))
