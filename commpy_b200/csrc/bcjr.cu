@@ -891,9 +891,9 @@ int cpb_map_decode(const cpbTrellis *t, const float *sys_dev, const float *par_d
     int S = 0;
     int rc = bcjr::check_trellis(t, &S);
     if (rc) return rc;
+    if (batch == 0) return CPB_OK;
     if (!sys_dev || !par_dev || !L_int_dev || !L_out_dev || batch < 0 || N < 1 || N > (1 << 24) || !(noise_variance > 0.0f))
         return CPB_EINVAL;
-    if (batch == 0) return CPB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t Fc = bcjr::chunk_frames(batch, (int)N, S);
     Scratch ws;

@@ -251,8 +251,8 @@ int cpb_modem_is_separable(const cpbModem *m) { return m ? m->separable : 0; }
 
 int cpb_demod_soft(const cpbModem *m, const float *y_dev, int64_t n_sym, float noise_var, float *llr_dev, void *stream)
 {
+    if (m && n_sym == 0) return CPB_OK;            // nothing to do: empty tensors carry null pointers
     if (!m || !y_dev || !llr_dev || n_sym < 0) return CPB_EINVAL;
-    if (n_sym == 0) return CPB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const float inv = demap::LOG2E / noise_var;
     const unsigned grid = (unsigned)ceil_div(n_sym, 256);
@@ -286,8 +286,8 @@ int cpb_demod_soft(const cpbModem *m, const float *y_dev, int64_t n_sym, float n
 
 int cpb_demod_hard(const cpbModem *m, const float *y_dev, int64_t n_sym, uint8_t *bits_dev, void *stream)
 {
+    if (m && n_sym == 0) return CPB_OK;
     if (!m || !y_dev || !bits_dev || n_sym < 0) return CPB_EINVAL;
-    if (n_sym == 0) return CPB_OK;
     const unsigned grid = (unsigned)ceil_div(n_sym, 256);
     demap::demod_hard_kernel<<<grid, 256, sizeof(float2) * m->M, (cudaStream_t)stream>>>(
         reinterpret_cast<const float2 *>(y_dev), n_sym, m->cst_dev, m->M, m->nb, bits_dev);

@@ -472,8 +472,8 @@ static int ldpc_dispatch(const cpbLdpc *h, void *llr_dev, int precision, int64_t
                          uint8_t *dec_dev, void *out_llr_dev, int32_t *iters_dev, void *workspace_dev,
                          size_t workspace_bytes, void *stream)
 {
+    if (h && batch == 0) return CPB_OK;
     if (!h || !llr_dev || !dec_dev || batch < 0 || n_iters < 0) return CPB_EINVAL;
-    if (batch == 0) return CPB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == CPB_LDPC_FP64)
         return ldpc::run<double>(h, reinterpret_cast<double *>(llr_dev), batch, n_iters, spa, dec_dev,

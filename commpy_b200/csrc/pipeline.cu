@@ -55,9 +55,9 @@ int ensure(PipeCtx &c, size_t need_in, size_t need_out)
 extern "C" int cpb_viterbi_decode_host(const cpbTrellis *t, const void *coded_host, int in_dtype, int64_t batch,
                                        int64_t n_in, int tb_depth, int mode, uint8_t *out_bits_host)
 {
-    if (!t || !coded_host || !out_bits_host || batch < 0 || n_in <= 0) return CPB_EINVAL;
     if (in_dtype != CPB_U8 && in_dtype != CPB_F32) return CPB_EINVAL;
-    if (batch == 0) return CPB_OK;
+    if (t && batch == 0) return CPB_OK;
+    if (!t || !coded_host || !out_bits_host || batch < 0 || n_in <= 0) return CPB_EINVAL;
     int64_t L = 0, T = 0;
     int rc = cpb_viterbi_sizes(t, n_in, &L, &T);
     if (rc) return rc;

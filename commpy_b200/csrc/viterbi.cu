@@ -871,8 +871,9 @@ int cpb_viterbi_decode(const cpbTrellis *t, const void *coded_dev, int in_dtype,
                        int tb_depth, int mode, uint8_t *out_bits_dev, void *workspace_dev, size_t workspace_bytes,
                        void *stream)
 {
-    if (!t || !coded_dev || !out_bits_dev || batch < 0 || n_in < 0) return CPB_EINVAL;
     if (mode < 0 || mode > 2) return CPB_EINVAL;        // ValueError of convcode.py:682-685
+    if (t && batch == 0) return CPB_OK;                 // empty tensors carry null pointers
+    if (!t || !coded_dev || !out_bits_dev || batch < 0 || n_in < 0) return CPB_EINVAL;
     if (in_dtype != CPB_U8 && in_dtype != CPB_F32) return CPB_EINVAL;
     if (mode != CPB_VITERBI_HARD && in_dtype != CPB_F32) return CPB_EINVAL;
     if (batch == 0) return CPB_OK;
