@@ -67,6 +67,7 @@ struct FFCode {
 using Code133_171 = FFCode<6, 0133, 0171>;   // the standard K=7 code (octal 133,171)
 using Code171_133 = FFCode<6, 0171, 0133>;
 using Code5_43 = FFCode<6, 5, 43>;           // what Trellis makes of DECIMAL (133,171): wifi80211.py:49 quirk
+using Code5_7 = FFCode<6, 5, 7>;             // the 64-state trellis of commpy/channelcoding/README.md:81-84 ([[5, 7]], memory 6)
 
 template <class CODE>
 static bool code_matches(const cpbTrellis &t)
@@ -779,6 +780,7 @@ int cpb_trellis_create(const int32_t *next_state, const int32_t *output, int k, 
     if (code_matches<Code133_171>(*t)) t->fast_id = 1;
     else if (code_matches<Code171_133>(*t)) t->fast_id = 2;
     else if (code_matches<Code5_43>(*t)) t->fast_id = 3;
+    else if (code_matches<Code5_7>(*t)) t->fast_id = 4;
     *out = t;
     return CPB_OK;
 }
@@ -916,11 +918,13 @@ int cpb_viterbi_decode(const cpbTrellis *t, const void *coded_dev, int in_dtype,
         if (pack == 2) {
             if (t->fast_id == 1) rc = fast::launch<Code133_171, 2>(p, st);
             else if (t->fast_id == 2) rc = fast::launch<Code171_133, 2>(p, st);
-            else rc = fast::launch<Code5_43, 2>(p, st);
+            else if (t->fast_id == 3) rc = fast::launch<Code5_43, 2>(p, st);
+            else rc = fast::launch<Code5_7, 2>(p, st);
         } else {
             if (t->fast_id == 1) rc = fast::launch<Code133_171, 1>(p, st);
             else if (t->fast_id == 2) rc = fast::launch<Code171_133, 1>(p, st);
-            else rc = fast::launch<Code5_43, 1>(p, st);
+            else if (t->fast_id == 3) rc = fast::launch<Code5_43, 1>(p, st);
+            else rc = fast::launch<Code5_7, 1>(p, st);
         }
         ws.release();
         return rc;

@@ -118,3 +118,45 @@ def test_wifi80211_link_performance_runs_on_gpu_path():
         BERs, BEs, CEs, NCs = w.link_performance(ch, snrs, 12, 1, 600, stop_on_surpass_error=False)
         assert BERs.shape == (2,) and BEs.shape == (2, 12) and NCs.sum() == 24
         assert BERs[0] > BERs[1] and BERs[1] < 0.05, (mcs, BERs)
+
+
+@pytest.mark.gpu
+def test_published_ber_of_reference_readme():
+    """commpy/channelcoding/README.md:81-163: QPSK, Trellis([6], [[5, 7]]), tb_depth = 5*(m+1) = 35, Eb/N0 = 5 dB,
+    10 x 1e5 bits.  Published: 'unquantized' 2.8e-5, 'hard' 7.81e-4, uncoded 9.064e-3."""
+    from commpy_b200.channelcoding import Trellis, viterbi_decode_batch
+    from commpy_b200.modulation import PSKModem
+    rs = np.random.RandomState(2024)
+    N, trials, M = 100000, 10, 4
+    k, rate = 2, 0.5
+    trellis = Trellis(np.array([6]), np.array([[5, 7]]))
+    modem = PSKModem(M)
+    tb_depth = 5 * (6 + 1)
+    EbNo = 5
+    snrdB = EbNo + 10 * np.log10(k * rate)
+    noiseVar = 10 ** (-snrdB / 10)
+    msgs = rs.randint(0, 2, (trials, N))
+    coded = helpers.encode_batch(msgs, trellis, "term")
+    soft_in, hard_in, unc_err = [], [], 0
+    for t in range(trials):
+        x = modem.modulate(coded[t])
+        xu = modem.modulate(msgs[t])
+        Es = np.mean(np.abs(x) ** 2)
+        No = Es / ((10 ** (EbNo / 10)) * np.log2(M))
+        noisy = x + np.sqrt(No / 2) * (rs.randn(len(x)) + 1j * rs.randn(len(x)))
+        noisy_u = xu + np.sqrt(No / 2) * (rs.randn(len(xu)) + 1j * rs.randn(len(xu)))
+        soft_in.append(modem.demodulate(noisy, "soft", noiseVar))
+        hard_in.append(modem.demodulate(noisy, "hard"))
+        unc_err += int((modem.demodulate(noisy_u, "hard") != msgs[t]).sum())
+    dec_soft = viterbi_decode_batch(np.stack(soft_in).astype(np.float32), trellis, tb_depth, "unquantized")
+    dec_hard = viterbi_decode_batch(np.stack(hard_in).astype(np.uint8), trellis, tb_depth, "hard")
+    ber_soft = (dec_soft[:, :N] != msgs).mean()
+    ber_hard = (dec_hard[:, :N] != msgs).mean()
+    ber_unc = unc_err / (trials * N)
+    assert abs(ber_unc - 9.064e-3) / 9.064e-3 < 0.05, ber_unc
+    assert abs(ber_hard - 7.81e-4) / 7.81e-4 < 0.25, ber_hard
+    assert 0.8e-5 < ber_soft < 8e-5, ber_soft
+    # and bit-exact with the oracle on the hard stream of one trial
+    from oracle import oracle
+    want = oracle.viterbi_decode(hard_in[0].astype(np.float64), trellis, tb_depth, "hard")
+    assert np.array_equal(dec_hard[0], want)
