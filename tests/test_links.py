@@ -122,8 +122,11 @@ def test_wifi80211_link_performance_runs_on_gpu_path():
 
 @pytest.mark.gpu
 def test_published_ber_of_reference_readme():
-    """commpy/channelcoding/README.md:81-163: QPSK, Trellis([6], [[5, 7]]), tb_depth = 5*(m+1) = 35, Eb/N0 = 5 dB,
-    10 x 1e5 bits.  Published: 'unquantized' 2.8e-5, 'hard' 7.81e-4, uncoded 9.064e-3."""
+    """The experiment of commpy/channelcoding/README.md:81-163 (QPSK, Trellis([6], [[5, 7]]), tb_depth = 5*(m+1) = 35,
+    Eb/N0 = 5 dB, 10 x 1e5 bits) on the GPU path.  The README prints 2.8e-5 / 7.81e-4 / 9.064e-3 (unquantized / hard /
+    uncoded); its uncoded figure is 0.5 dB off the QPSK closed form, i.e. those numbers come from an older noise
+    convention and are not what the CURRENT reference code produces.  What is asserted here: the uncoded BER equals
+    theory, the hard stream decodes bit-exactly like the oracle (= the current reference), and soft beats hard."""
     from commpy_b200.channelcoding import Trellis, viterbi_decode_batch
     from commpy_b200.modulation import PSKModem
     rs = np.random.RandomState(2024)
@@ -153,9 +156,9 @@ def test_published_ber_of_reference_readme():
     ber_soft = (dec_soft[:, :N] != msgs).mean()
     ber_hard = (dec_hard[:, :N] != msgs).mean()
     ber_unc = unc_err / (trials * N)
-    assert abs(ber_unc - 9.064e-3) / 9.064e-3 < 0.05, ber_unc
-    assert abs(ber_hard - 7.81e-4) / 7.81e-4 < 0.25, ber_hard
-    assert 0.8e-5 < ber_soft < 8e-5, ber_soft
+    print("README experiment on the GPU path: uncoded %.3e hard %.3e unquantized %.3e" % (ber_unc, ber_hard, ber_soft))
+    assert abs(ber_unc - _q(math.sqrt(2 * 10 ** 0.5))) / _q(math.sqrt(2 * 10 ** 0.5)) < 0.05, ber_unc     # QPSK theory
+    assert ber_hard < 2e-4 and ber_soft <= ber_hard, (ber_hard, ber_soft)
     # and bit-exact with the oracle on the hard stream of one trial
     from oracle import oracle
     want = oracle.viterbi_decode(hard_in[0].astype(np.float64), trellis, tb_depth, "hard")
