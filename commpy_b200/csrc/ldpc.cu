@@ -21,6 +21,7 @@
 // the reference's order and no multiply exists to be contracted into an FMA, so decisions, iteration counts
 // and out_llrs equal the float64 reference bit for bit.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -52,6 +53,15 @@ __device__ __forceinline__ VT ld16(const void *p)
     w[0] = a; w[1] = b; w[2] = c; w[3] = d;
     return v;
 }
+
+// R (check-to-variable messages) is stored chunk-major: [frame chunk][edge][RS frames], RS = frames per chunk
+// (RS = F, one chunk, unless the bulk-copy check pass is in use), so that the rows of one check node and one
+// chunk are contiguous.
+struct RLayout {
+    int RS;                // frames per chunk (row stride)
+    int64_t chunk_elems;   // nnz * RS
+    template <typename T> __device__ __forceinline__ T *at(T *R, int64_t f) const { return R + (f / RS) * chunk_elems + (f % RS); }
+};
 
 struct State {
     int32_t *unsat_iter;   // [F] last iteration (1-based) at which an unsatisfied check was seen
@@ -127,7 +137,7 @@ __global__ void finish_iters_kernel(const State st, int64_t batch, int n_iters, 
 template <typename T, int DEGMAX>
 __global__ void __launch_bounds__(256) cn_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
                                                  int m, int64_t F, int iter, const T *__restrict__ post,
-                                                 T *__restrict__ R, const State st)
+                                                 T *__restrict__ Rbase, const State st, const RLayout rl)
 {
     using VT = typename VecOf<T>::type;
     constexpr int V = VecOf<T>::V;
@@ -137,6 +147,8 @@ __global__ void __launch_bounds__(256) cn_kernel(const int32_t *__restrict__ row
     if (gid >= (int64_t)m * G) return;
     const int i = (int)(gid / G);
     const int64_t f = (gid - (int64_t)i * G) * V;
+    T *const Rf = rl.at(Rbase, f);
+    const int64_t RS = rl.RS;
     bool act[V];
     bool any = false;
 #pragma unroll
@@ -159,7 +171,7 @@ __global__ void __launch_bounds__(256) cn_kernel(const int32_t *__restrict__ row
 #pragma unroll
         for (int k = 0; k < QN; ++k) {
             pv[k] = *reinterpret_cast<const VT *>(post + (int64_t)cix[k] * F + f);
-            q[k] = *reinterpret_cast<const VT *>(R + (int64_t)min(e0 + k, e1 - 1) * F + f);
+            q[k] = *reinterpret_cast<const VT *>(Rf + (int64_t)min(e0 + k, e1 - 1) * RS);
         }
 #pragma unroll
         for (int k = 0; k < QN; ++k) {
@@ -182,7 +194,7 @@ __global__ void __launch_bounds__(256) cn_kernel(const int32_t *__restrict__ row
         for (int e = e0; e < e1; ++e) {
             const int c = __ldg(&col_idx[e]);
             const VT p = *reinterpret_cast<const VT *>(post + (int64_t)c * F + f);
-            const VT r = *reinterpret_cast<const VT *>(R + (int64_t)e * F + f);
+            const VT r = *reinterpret_cast<const VT *>(Rf + (int64_t)e * RS);
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 par[v] ^= signbit(p.v[v]) ? 1 : 0;
@@ -207,7 +219,7 @@ __global__ void __launch_bounds__(256) cn_kernel(const int32_t *__restrict__ row
                 bool all = true;
 #pragma unroll
                 for (int v = 0; v < V; ++v) all &= act[v];
-                if (!all) r = *reinterpret_cast<const VT *>(R + (int64_t)e * F + f);     // keep finished frames' messages
+                if (!all) r = *reinterpret_cast<const VT *>(Rf + (int64_t)e * RS);     // keep finished frames' messages
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     const T x = q[k].v[v];
@@ -216,14 +228,14 @@ __global__ void __launch_bounds__(256) cn_kernel(const int32_t *__restrict__ row
                     const T val = (ng & 1) ? -mag : mag;                      // prod of sign(others)
                     if (act[v]) r.v[v] = val;
                 }
-                *reinterpret_cast<VT *>(R + (int64_t)e * F + f) = r;
+                *reinterpret_cast<VT *>(Rf + (int64_t)e * RS) = r;
             }
         }
     } else {
         for (int e = e0; e < e1; ++e) {
             const int c = __ldg(&col_idx[e]);
             const VT p = *reinterpret_cast<const VT *>(post + (int64_t)c * F + f);
-            VT r = *reinterpret_cast<const VT *>(R + (int64_t)e * F + f);
+            VT r = *reinterpret_cast<const VT *>(Rf + (int64_t)e * RS);
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 const T x = p.v[v] - r.v[v];
@@ -232,10 +244,247 @@ __global__ void __launch_bounds__(256) cn_kernel(const int32_t *__restrict__ row
                 const T val = (ng & 1) ? -mag : mag;
                 if (act[v]) r.v[v] = val;
             }
-            *reinterpret_cast<VT *>(R + (int64_t)e * F + f) = r;
+            *reinterpret_cast<VT *>(Rf + (int64_t)e * RS) = r;
         }
     }
 }
+
+// ---- check pass staged through shared memory by the bulk-copy engine (TMA, cp.async.bulk) -------------------------------
+// With frames innermost, the messages of one edge for a chunk of FT frames are ONE contiguous row of FT*sizeof(T) bytes
+// (1 KB at FT = 256 floats), and so is the posterior row the edge gathers.  A persistent CTA therefore walks tiles
+// (check node i, frame chunk c): warp 0 asks the copy engine for the 2*deg rows of a tile (lane k <-> edge k) and an
+// mbarrier counts the bytes as they land; FT threads (one frame each) run the two-minimum update on the staged rows in
+// place; warp 0 hands the R rows back to the copy engine (bulk store).  NSTAGE tiles rotate, loads run NSTAGE-2 tiles
+// ahead, so the memory system always holds several KB per CTA in flight without a register being spent on it -- the
+// register-staged kernel above tops out at ~3.3 TB/s because its loads, math and stores share 16 warps per SM.
+// Same arithmetic, same order: results are bit-identical to cn_kernel.
+namespace bulk {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void load_row(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void store_row(void *dst, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int MAXDEG = 32;      // lane k of the producer warp owns edge k
+constexpr int NSTAGE = 6;       // tiles resident in shared memory
+constexpr int LAG = 4;          // a tile's rows are stored LAG tiles after its loads were issued
+
+// Min-sum update of one staged row for one frame: rs[k*FT] = R_ik (in/out), ps[k*FT] = posterior of the edge's variable.
+// Same operations in the same order as cn_kernel (Q = post - R; first minimum keeps the lowest edge index; a message's
+// sign is the parity of the strictly negative OTHER Q's), written without data-dependent branches.
+// Returns the syndrome parity of the row (signbit of the posteriors, ldpc.py:193,205).
+template <typename T, int DEG>
+__device__ __forceinline__ int consume_row(T *rs, const T *ps, int FT, bool act)
+{
+    T x[DEG];
+    T min1 = (T)INFINITY, min2 = (T)INFINITY;
+    int arg = -1, par = 0;
+    unsigned negmask = 0;
+#pragma unroll
+    for (int k = 0; k < DEG; ++k) {
+        const T p = ps[(size_t)k * FT];
+        par ^= signbit(p) ? 1 : 0;
+        x[k] = p - rs[(size_t)k * FT];                       // Q_ij = (tot_j + llr_j) - R_ij, ldpc.py:244-245
+    }
+#pragma unroll
+    for (int k = 0; k < DEG; ++k) {
+        const T a = fabs(x[k]);
+        if (x[k] < (T)0) negmask |= 1u << k;
+        const bool lt = a < min1;
+        min2 = fmin(min2, fmax(a, min1));
+        min1 = fmin(min1, a);
+        arg = lt ? k : arg;
+    }
+    if (act) {
+        const unsigned flip = (__popc(negmask) & 1) ? ~negmask : negmask;   // bit k: odd number of negative OTHER messages
+#pragma unroll
+        for (int k = 0; k < DEG; ++k) {
+            const T mag = (k == arg) ? min2 : min1;              // min over the OTHER edges (:238)
+            rs[(size_t)k * FT] = ((flip >> k) & 1u) ? -mag : mag;   // prod of sign(others)
+        }
+    }
+    return par;
+}
+
+template <typename T>
+__device__ __forceinline__ int consume_row_any(T *rs, const T *ps, int FT, int deg, bool act)
+{
+    T min1 = (T)INFINITY, min2 = (T)INFINITY;
+    int arg = -1, neg = 0, par = 0;
+    for (int k = 0; k < deg; ++k) {
+        const T p = ps[(size_t)k * FT];
+        par ^= signbit(p) ? 1 : 0;
+        const T x = p - rs[(size_t)k * FT];
+        const T a = fabs(x);
+        neg += (x < (T)0) ? 1 : 0;
+        if (a < min1) { min2 = min1; min1 = a; arg = k; }
+        else if (a < min2) min2 = a;
+    }
+    if (act) {
+        for (int k = 0; k < deg; ++k) {
+            const T x = ps[(size_t)k * FT] - rs[(size_t)k * FT];
+            const T mag = (k == arg) ? min2 : min1;
+            const int ng = neg - ((x < (T)0) ? 1 : 0);
+            rs[(size_t)k * FT] = (ng & 1) ? -mag : mag;
+        }
+    }
+    return par;
+}
+
+// CTA = FT consumer threads (one frame each) + one producer warp.  A CTA owns one frame chunk and every
+// (gridDim.x / nchunks)-th check node.  Producer step t:  wait until the consumers are done with tile t-LAG, bulk-store
+// its R rows;  wait until the stores of tile t-NSTAGE have left shared memory, bulk-load tile t into that stage.
+// Consumers: wait for the bytes of tile t, update the rows in place, signal the producer.  No block-wide barrier.
+template <typename T>
+__global__ void __launch_bounds__(288) cn_bulk_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
+                                                      int m, int64_t F, int iter, const T *__restrict__ post,
+                                                      T *__restrict__ R, const State st, int nchunks, int maxdeg, int64_t nnz)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int FT = blockDim.x - 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncw = FT >> 5;                                     // consumer warps
+    const size_t stage_elems = (size_t)2 * maxdeg * FT;
+    T *tiles = reinterpret_cast<T *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NSTAGE * stage_elems * sizeof(T));
+    uint64_t *comp = full + NSTAGE;
+    int *info = reinterpret_cast<int *>(comp + NSTAGE);          // [NSTAGE][2]: degree, first edge
+    const int c = (int)(blockIdx.x % nchunks);                   // frame chunk of this CTA
+    const int i0 = (int)(blockIdx.x / nchunks), istride = (int)(gridDim.x / nchunks);
+    const int mine = (i0 < m) ? (m - i0 + istride - 1) / istride : 0;
+    const int64_t f0 = (int64_t)c * FT;
+    const int nfr = (int)min((int64_t)FT, F - f0);
+    const uint32_t row_bytes = (uint32_t)nfr * (uint32_t)sizeof(T);
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&comp[s], ncw); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // frames that already satisfied their syndrome are frozen (ldpc.py:205): a chunk without a live frame is skipped
+    bool act = false;
+    if (tid < nfr) act = st.done[f0 + tid] == 0;
+    const int any_live = __syncthreads_or(act ? 1 : 0);
+    if (!any_live || mine == 0) return;
+
+    if (warp == ncw) {
+        // ------------------------------------------------ producer warp
+        // R is chunk-major, so the deg rows of a tile are one contiguous block: one bulk load and one bulk store per tile
+        // (lane 0), plus one bulk load per gathered posterior row (lane k <-> edge k).
+        T *const Rc = R + (int64_t)c * nnz * FT;
+        // index prefetch: row_ptr two tiles ahead, col_idx one tile ahead, so no step waits on a dependent load
+        int e0_n, e1_n, col_n, e0_nn = 0, e1_nn = 0;
+        e0_n = __ldg(&row_ptr[i0]); e1_n = __ldg(&row_ptr[i0 + 1]);
+        col_n = (lane < e1_n - e0_n) ? __ldg(&col_idx[e0_n + lane]) : 0;
+        if (mine > 1) { e0_nn = __ldg(&row_ptr[i0 + istride]); e1_nn = __ldg(&row_ptr[i0 + istride + 1]); }
+        for (int t = 0; t < mine + LAG; ++t) {
+            const int u = t - LAG;
+            if (u >= 0) {                                        // store tile u
+                const int su = u % NSTAGE;
+                mbar_wait(&comp[su], (uint32_t)((u / NSTAGE) & 1));
+                if (lane == 0) {
+                    const int deg = info[su * 2 + 0], e0 = info[su * 2 + 1];
+                    store_row(Rc + (int64_t)e0 * FT, tiles + (size_t)su * stage_elems, (uint32_t)deg * row_bytes);
+                }
+                commit_group();
+            }
+            if (t < mine) {                                      // load tile t
+                const int s = t % NSTAGE;
+                const int e0 = e0_n, deg = e1_n - e0_n, col = col_n;
+                if (t + 1 < mine) {
+                    e0_n = e0_nn; e1_n = e1_nn;
+                    col_n = (lane < e1_n - e0_n) ? __ldg(&col_idx[e0_n + lane]) : 0;
+                    if (t + 2 < mine) {
+                        const int i = i0 + (t + 2) * istride;
+                        e0_nn = __ldg(&row_ptr[i]); e1_nn = __ldg(&row_ptr[i + 1]);
+                    }
+                }
+                wait_group_read<NSTAGE - LAG>();                 // stores of tile t-NSTAGE have been read out of this stage
+                T *rs = tiles + (size_t)s * stage_elems;
+                if (lane == 0) {
+                    info[s * 2 + 0] = deg; info[s * 2 + 1] = e0;
+                    mbar_expect_tx(&full[s], 2u * (uint32_t)deg * row_bytes);
+                    load_row(rs, Rc + (int64_t)e0 * FT, (uint32_t)deg * row_bytes, &full[s]);
+                }
+                __syncwarp();
+                if (lane < deg)
+                    load_row(rs + (size_t)(maxdeg + lane) * FT, post + (int64_t)col * F + f0, row_bytes, &full[s]);
+            }
+        }
+        wait_group_read<0>();               // shared memory must outlive the last stores
+        return;
+    }
+
+    // ---------------------------------------------------- consumers: thread <-> frame f0 + tid
+    const bool valid = tid < nfr;
+    const int64_t f = f0 + tid;
+    int unsat = 0;
+    for (int t = 0; t < mine; ++t) {
+        const int s = t % NSTAGE;
+        mbar_wait(&full[s], (uint32_t)((t / NSTAGE) & 1));
+        const int deg = info[s * 2 + 0];
+        T *rs = tiles + (size_t)s * stage_elems + tid;
+        const T *ps = rs + (size_t)maxdeg * FT;
+        if (valid) {
+            int par;
+            switch (deg) {                      // warp-uniform: fully unrolled bodies for the common short rows
+            case 2: par = consume_row<T, 2>(rs, ps, FT, act); break;
+            case 3: par = consume_row<T, 3>(rs, ps, FT, act); break;
+            case 4: par = consume_row<T, 4>(rs, ps, FT, act); break;
+            case 5: par = consume_row<T, 5>(rs, ps, FT, act); break;
+            case 6: par = consume_row<T, 6>(rs, ps, FT, act); break;
+            case 7: par = consume_row<T, 7>(rs, ps, FT, act); break;
+            case 8: par = consume_row<T, 8>(rs, ps, FT, act); break;
+            default: par = consume_row_any<T>(rs, ps, FT, deg, act); break;
+            }
+            unsat |= par;
+        }
+        fence_proxy_async();                // the copy engine must see the rows just written
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&comp[s]);
+    }
+    // one flag store per frame and CTA (every writer stores the same value)
+    if (valid && act && unsat && st.unsat_iter[f] != iter + 1) st.unsat_iter[f] = iter + 1;
+}
+
+template <typename T>
+static size_t smem_bytes(int maxdeg, int FT)
+{
+    return (size_t)NSTAGE * 2 * maxdeg * FT * sizeof(T) + (size_t)NSTAGE * (2 * sizeof(uint64_t) + 2 * sizeof(int));
+}
+
+}  // namespace bulk
 
 // Sum-product check node (ldpc.py:209-227): t = tanh(Q/2), R_ij = 2 atanh(clip((prod_row t) / t_ij, -1, 1)) clipped to
 // +-500.  Same formula as the reference (product of the whole row divided by the edge's own factor); the product is
@@ -243,7 +492,7 @@ __global__ void __launch_bounds__(256) cn_kernel(const int32_t *__restrict__ row
 template <typename T>
 __global__ void __launch_bounds__(256) cn_spa_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
                                                      int m, int64_t F, int iter, const T *__restrict__ post,
-                                                     T *__restrict__ R, const State st)
+                                                     T *__restrict__ Rbase, const State st, const RLayout rl)
 {
     using VT = typename VecOf<T>::type;
     constexpr int V = VecOf<T>::V;
@@ -252,6 +501,8 @@ __global__ void __launch_bounds__(256) cn_spa_kernel(const int32_t *__restrict__
     if (gid >= (int64_t)m * G) return;
     const int i = (int)(gid / G);
     const int64_t f = (gid - (int64_t)i * G) * V;
+    T *const Rf = rl.at(Rbase, f);
+    const int64_t RS = rl.RS;
     bool act[V];
     bool any = false;
 #pragma unroll
@@ -265,7 +516,7 @@ __global__ void __launch_bounds__(256) cn_spa_kernel(const int32_t *__restrict__
     for (int e = e0; e < e1; ++e) {
         const int c = __ldg(&col_idx[e]);
         const VT p = *reinterpret_cast<const VT *>(post + (int64_t)c * F + f);
-        const VT r = *reinterpret_cast<const VT *>(R + (int64_t)e * F + f);
+        const VT r = *reinterpret_cast<const VT *>(Rf + (int64_t)e * RS);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             par[v] ^= signbit(p.v[v]) ? 1 : 0;
@@ -278,7 +529,7 @@ __global__ void __launch_bounds__(256) cn_spa_kernel(const int32_t *__restrict__
     for (int e = e0; e < e1; ++e) {
         const int c = __ldg(&col_idx[e]);
         const VT p = *reinterpret_cast<const VT *>(post + (int64_t)c * F + f);
-        VT r = *reinterpret_cast<const VT *>(R + (int64_t)e * F + f);
+        VT r = *reinterpret_cast<const VT *>(Rf + (int64_t)e * RS);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             const T t = tanh((p.v[v] - r.v[v]) * (T)0.5);
@@ -288,14 +539,15 @@ __global__ void __launch_bounds__(256) cn_spa_kernel(const int32_t *__restrict__
             x = x > (T)500 ? (T)500 : (x < (T)-500 ? (T)-500 : x);
             if (act[v]) r.v[v] = x;
         }
-        *reinterpret_cast<VT *>(R + (int64_t)e * F + f) = r;
+        *reinterpret_cast<VT *>(Rf + (int64_t)e * RS) = r;
     }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) vn_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ col_edge,
                                                  int n, int64_t F, int iter, const T *__restrict__ llrT,
-                                                 const T *__restrict__ R, T *__restrict__ post, const State st)
+                                                 const T *__restrict__ Rbase, T *__restrict__ post, const State st,
+                                                 const RLayout rl)
 {
     using VT = typename VecOf<T>::type;
     constexpr int V = VecOf<T>::V;
@@ -304,6 +556,8 @@ __global__ void __launch_bounds__(256) vn_kernel(const int32_t *__restrict__ col
     if (gid >= (int64_t)n * G) return;
     const int j = (int)(gid / G);
     const int64_t f = (gid - (int64_t)j * G) * V;
+    const T *const Rf = rl.at(Rbase, f);
+    const int64_t RS = rl.RS;
     bool act[V];
     bool any = false;
 #pragma unroll
@@ -324,7 +578,7 @@ __global__ void __launch_bounds__(256) vn_kernel(const int32_t *__restrict__ col
     for (int v = 0; v < V; ++v) tot[v] = (T)0;
     for (int q = c0; q < c1; ++q) {             // ascending check index = the reference's summation order
         const int e = __ldg(&col_edge[q]);
-        const VT r = *reinterpret_cast<const VT *>(R + (int64_t)e * F + f);
+        const VT r = *reinterpret_cast<const VT *>(Rf + (int64_t)e * RS);
 #pragma unroll
         for (int v = 0; v < V; ++v) tot[v] += r.v[v];
     }
@@ -386,11 +640,39 @@ static int run(const cpbLdpc *h, T *llr, int64_t batch, int n_iters, int spa, ui
         const int64_t G = F / V;
         const unsigned cn_blocks = (unsigned)ceil_div((int64_t)h->m * G, 256);
         const unsigned vn_blocks = (unsigned)ceil_div((int64_t)h->n * G, 256);
+        // bulk-copy staged check pass: min-sum, row degree <= 32, frame chunks of 256 or 128
+        bool use_bulk = !spa && h->max_row_deg <= bulk::MAXDEG && !getenv("CPB_LDPC_NO_BULK");
+        int FT = (F % 256 == 0) ? 256 : ((F % 128 == 0) ? 128 : 0);
+        { const char *e_ft = getenv("CPB_LDPC_FT"); if (e_ft && F % atoi(e_ft) == 0) FT = atoi(e_ft); }
+        int nchunks = 0, bulk_grid = 0;
+        size_t bulk_smem = 0;
+        if (FT == 0) use_bulk = false;
+        if (use_bulk) {
+            nchunks = (int)(F / FT);
+            bulk_smem = bulk::smem_bytes<T>(h->max_row_deg, FT);
+            if (bulk_smem > 200 * 1024) {
+                use_bulk = false;
+            } else {
+                e = cudaFuncSetAttribute(bulk::cn_bulk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem);
+                if (e != cudaSuccess) { ws.release(); return record_cuda_error(e, "cudaFuncSetAttribute", __FILE__, __LINE__); }
+                const DeviceProps &dp = device_props();
+                const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(220 * 1024) / (bulk_smem + 1024)));
+                int64_t want = (int64_t)(dp.sm_count > 0 ? dp.sm_count : 148) * per_sm;
+                want = std::max<int64_t>(nchunks, (want / nchunks) * nchunks);        // a multiple of nchunks
+                bulk_grid = (int)std::min<int64_t>((int64_t)h->m * nchunks, want);
+            }
+        }
+        RLayout rl;
+        rl.RS = use_bulk ? FT : (int)F;
+        rl.chunk_elems = (int64_t)h->nnz * rl.RS;
         for (int it = 0; it < n_iters; ++it) {
-            if (spa) cn_spa_kernel<T><<<cn_blocks, 256, 0, st>>>(h->row_ptr, h->col_idx, h->m, F, it, post, R, s);
-            else if (h->max_row_deg <= 8) cn_kernel<T, 8><<<cn_blocks, 256, 0, st>>>(h->row_ptr, h->col_idx, h->m, F, it, post, R, s);
-            else cn_kernel<T, 0><<<cn_blocks, 256, 0, st>>>(h->row_ptr, h->col_idx, h->m, F, it, post, R, s);
-            vn_kernel<T><<<vn_blocks, 256, 0, st>>>(h->col_ptr, h->col_edge, h->n, F, it, llrT, R, post, s);
+            if (use_bulk)
+                bulk::cn_bulk_kernel<T><<<bulk_grid, FT + 32, bulk_smem, st>>>(h->row_ptr, h->col_idx, h->m, F, it, post, R, s, nchunks,
+                                                                             h->max_row_deg, (int64_t)h->nnz);
+            else if (spa) cn_spa_kernel<T><<<cn_blocks, 256, 0, st>>>(h->row_ptr, h->col_idx, h->m, F, it, post, R, s, rl);
+            else if (h->max_row_deg <= 8) cn_kernel<T, 8><<<cn_blocks, 256, 0, st>>>(h->row_ptr, h->col_idx, h->m, F, it, post, R, s, rl);
+            else cn_kernel<T, 0><<<cn_blocks, 256, 0, st>>>(h->row_ptr, h->col_idx, h->m, F, it, post, R, s, rl);
+            vn_kernel<T><<<vn_blocks, 256, 0, st>>>(h->col_ptr, h->col_edge, h->n, F, it, llrT, R, post, s, rl);
         }
         store_kernel<T><<<tgrid, 256, 0, st>>>(post, nb, h->n, F, dec + f0 * h->n, out_llr ? out_llr + f0 * h->n : nullptr);
         if (iters_out)

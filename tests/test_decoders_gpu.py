@@ -5,6 +5,7 @@ from itertools import product
 
 import numpy as np
 import pytest
+import torch
 
 import helpers
 from oracle import oracle
@@ -149,6 +150,34 @@ def test_ldpc_fp32_converged_frames_match():
     assert np.array_equal(dec64.cpu().numpy(), want_dec)
     assert np.array_equal(out64.cpu().numpy(), want_out)
     assert np.array_equal(it64.cpu().numpy(), want_it)
+
+
+@pytest.mark.parametrize("batch", [256, 384])
+def test_ldpc_bulk_copy_check_pass_exact(batch, monkeypatch):
+    """Batches of >= 128 frames run the check pass staged by the bulk-copy engine (cn_bulk_kernel, chunk-major R):
+    fp64 stays bit-exact with the reference on every frame (converged or not), and fp32 output is bit-identical to the
+    register-staged kernels (same operations in the same order)."""
+    g, params, _ = _golden_ldpc(3)                    # WiMax 1440.720
+    n = params["n_vnodes"]
+    rs = np.random.RandomState(99 + batch)
+    sigma = 1.0 / np.sqrt(2 * 0.5 * 10 ** (1.6 / 10))
+    llr = (2.0 * (1.0 + sigma * rs.randn(batch, n)) / sigma ** 2)
+    llr[5] = 2.0 * (1.0 + 3.0 * rs.randn(n))          # a frame that never converges
+    want_dec, want_out, want_it = oracle.ldpc_bp_decode(llr.reshape(-1).copy(), params, "MSA", 20, return_iters=True,
+                                                        threads=8)
+    want_dec = want_dec.reshape(n, batch).T
+    want_out = want_out.reshape(n, batch).T
+    assert (want_it < 20).sum() > batch // 4 and (want_it == 20).sum() >= 1
+    monkeypatch.delenv("CPB_LDPC_NO_BULK", raising=False)
+    dec64, out64, it64 = ldpc_bp_decode_batch(llr.copy(), params, 20, "fp64", return_iters=True)
+    assert np.array_equal(dec64.cpu().numpy(), want_dec)
+    assert np.array_equal(out64.cpu().numpy(), want_out)
+    assert np.array_equal(it64.cpu().numpy(), want_it)
+    dec32, out32, it32 = ldpc_bp_decode_batch(llr.astype(np.float32), params, 20, "fp32", return_iters=True)
+    monkeypatch.setenv("CPB_LDPC_NO_BULK", "1")
+    dec32r, out32r, it32r = ldpc_bp_decode_batch(llr.astype(np.float32), params, 20, "fp32", return_iters=True)
+    assert torch.equal(dec32, dec32r) and torch.equal(it32, it32r)
+    assert torch.equal(out32.view(torch.int32), out32r.view(torch.int32))
 
 
 def test_ldpc_noiseless_roundtrip_and_zero_iterations():
