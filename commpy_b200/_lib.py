@@ -21,7 +21,7 @@ SYMBOLS = [
     "cpb_map_decode", "cpb_turbo_decode",
     "cpb_ldpc_create", "cpb_ldpc_destroy", "cpb_ldpc_workspace_bytes", "cpb_ldpc_minsum", "cpb_ldpc_sumproduct",
     "cpb_modem_create", "cpb_modem_destroy", "cpb_modem_is_separable", "cpb_demod_soft", "cpb_demod_hard",
-    "cpb_count_errors",
+    "cpb_count_errors", "cpb_conv_link_tx",
 ]
 
 _lib = None

@@ -200,6 +200,12 @@ __global__ void __launch_bounds__(256) demod_hard_kernel(const float2 *__restric
 
 }  // namespace demap
 
+// accessor for the other translation units (not part of the C-ABI)
+void cpb_modem_info(const cpbModem *m, int *M, int *nb, const float **cst_dev)
+{
+    *M = m->M; *nb = m->nb; *cst_dev = reinterpret_cast<const float *>(m->cst_dev);
+}
+
 extern "C" {
 
 int cpb_modem_create(const double *constellation, int M, cpbModem **out)

@@ -1,0 +1,207 @@
+// Transmit side of a coded AWGN link, generated on the device -- the caller of the hot path, SURVEY 8(f) row 1.
+// One kernel replaces, for a batch of frames, what LinkModel.link_performance does per frame on the host:
+//     msg = randint(0, 2, send_chunk)                         commpy/links.py:318
+//     coded = conv_encode(msg, trellis, 'cont')               commpy/channelcoding/convcode.py:475-558 (loop :535-540)
+//     symbols = modem.modulate(coded)                         commpy/modulation.py:79-98 (MSB-first index, :93-96)
+//     y = symbols + noise                                     commpy/channels.py:181-221, noise scale :53,:74
+// so that 1e8-symbol BER points (BASELINE config 5) never touch the host.  Nothing here is on the parity path: the
+// message bits are returned, and the receiver (cpb_demod_soft -> cpb_viterbi_decode -> cpb_count_errors) is what is
+// checked against the oracle.
+//
+// Randomness is counter based (Philox4x32-10): message bit i of global frame f is bit (i & 127) of
+// Philox(counter = (f_lo, f_hi, i >> 7, 0), key = seed); the noise of symbols 2q, 2q+1 of frame f comes from
+// Philox(counter = (f_lo, f_hi, q, 1), key = seed) through Box-Muller.  Results therefore do not depend on the launch
+// geometry, the batch split or the number of GPUs (each rank passes its own first_frame), SURVEY 8(e).
+//
+// Encoder: k = 1 feed-forward shift register; tap mask g_j bit b multiplies the input delayed by b (bit 0 = current
+// input) -- derived on the host from the Trellis tables and verified against every (state, input) entry.
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace cpb;
+
+struct cpbTrellis;
+struct cpbModem;
+void cpb_trellis_dims(const cpbTrellis *t, int *k, int *n, int *S);
+void cpb_trellis_host_tables(const cpbTrellis *t, const int32_t **next, const int32_t **out);
+void cpb_modem_info(const cpbModem *m, int *M, int *nb, const float **cst_dev);
+
+namespace txlink {
+
+struct Params {
+    uint32_t g[8];            // tap masks, n <= 8
+    int n, mem;               // outputs per input bit, memory M
+    int nb, Mc;               // bits per symbol, constellation size
+    int64_t frames, frame_bits, nsym;   // per frame: information bits, symbols
+    int64_t first_frame;
+    uint32_t seed_lo, seed_hi;
+    float sigma;              // per real component
+    int spt;                  // symbols per thread
+    int64_t chunks;           // threads per frame
+    const float2 *cst;
+    uint8_t *msg;
+    float2 *y;
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// two uint32 -> two standard normals (Box-Muller); u1 in (0, 1]
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b)
+{
+    const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float u2 = (float)b * 2.3283064365386963e-10f;
+    const float r = sqrtf(-2.0f * __logf(u1));
+    float sn, cs;
+    __sincosf(6.283185307179586f * u2, &sn, &cs);
+    return make_float2(r * cs, r * sn);
+}
+
+__global__ void __launch_bounds__(128) conv_link_tx_kernel(const Params p)
+{
+    extern __shared__ float2 s_cst[];
+    for (int k = threadIdx.x; k < p.Mc; k += blockDim.x) s_cst[k] = p.cst[k];
+    __syncthreads();
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= p.frames * p.chunks) return;
+    const int64_t fl = gid / p.chunks;                       // frame within this call
+    const int64_t ch = gid - fl * p.chunks;
+    const uint64_t fg = (uint64_t)(p.first_frame + fl);      // global frame id
+    const uint32_t f_lo = (uint32_t)fg, f_hi = (uint32_t)(fg >> 32);
+    const int64_t s0 = ch * p.spt;
+    const int64_t s1 = min(s0 + (int64_t)p.spt, p.nsym);
+    int64_t i = s0 * p.nb / p.n;                             // first information bit (s0 * nb is a multiple of n)
+
+    uint32_t blk_id = 0xffffffffu;
+    uint4 blk = make_uint4(0, 0, 0, 0);
+    auto get_bit = [&](int64_t idx) -> uint32_t {
+        const uint32_t b = (uint32_t)(idx >> 7);
+        if (b != blk_id) { blk = philox4x32_10(make_uint4(f_lo, f_hi, b, 0u), p.seed_lo, p.seed_hi); blk_id = b; }
+        const uint32_t w = (uint32_t)(idx >> 5) & 3u;
+        const uint32_t word = (w == 0) ? blk.x : (w == 1) ? blk.y : (w == 2) ? blk.z : blk.w;
+        return (word >> ((uint32_t)idx & 31u)) & 1u;
+    };
+
+    // shift register before bit i: bit b = u_{i-1-b}; the encoder starts in state 0 (convcode.py:529)
+    uint32_t reg = 0;
+    for (int b = 0; b < p.mem; ++b)
+        if (i - 1 - b >= 0) reg |= get_bit(i - 1 - b) << b;
+    const uint32_t regmask = (2u << p.mem) - 1u;
+
+    uint8_t *msg = p.msg + fl * p.frame_bits;
+    float2 *y = p.y + fl * p.nsym;
+    const bool pack4 = ((p.frame_bits & 3) == 0) && ((i & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.msg) & 3) == 0);
+    uint32_t mword = 0;
+    uint64_t acc = 0;
+    int nacc = 0;
+    int64_t sym = s0;
+    float2 spare = make_float2(0.f, 0.f);
+    while (sym < s1) {
+        const uint32_t u = get_bit(i);
+        reg = ((reg << 1) | u) & regmask;
+        if (pack4) {
+            mword |= u << (8 * ((uint32_t)i & 3u));
+            if (((uint32_t)i & 3u) == 3u) { *reinterpret_cast<uint32_t *>(msg + (i - 3)) = mword; mword = 0; }
+        } else {
+            msg[i] = (uint8_t)u;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < p.n) acc = (acc << 1) | (uint64_t)(__popc(reg & p.g[j]) & 1);
+        nacc += p.n;
+        ++i;
+        while (nacc >= p.nb && sym < s1) {
+            nacc -= p.nb;
+            const uint32_t idx = (uint32_t)(acc >> nacc) & (uint32_t)(p.Mc - 1);      // first coded bit = MSB (modulation.py:93-96)
+            float2 nz;
+            if ((sym & 1) == 0) {
+                const uint4 r = philox4x32_10(make_uint4(f_lo, f_hi, (uint32_t)(sym >> 1), 1u), p.seed_lo, p.seed_hi);
+                nz = box_muller(r.x, r.y);
+                spare = box_muller(r.z, r.w);
+            } else {
+                if (sym == s0) {               // (cannot happen: chunks start on even symbols) kept for safety
+                    const uint4 r = philox4x32_10(make_uint4(f_lo, f_hi, (uint32_t)(sym >> 1), 1u), p.seed_lo, p.seed_hi);
+                    spare = box_muller(r.z, r.w);
+                }
+                nz = spare;
+            }
+            const float2 c = s_cst[idx];
+            y[sym] = make_float2(fmaf(p.sigma, nz.x, c.x), fmaf(p.sigma, nz.y, c.y));
+            ++sym;
+        }
+    }
+    if (pack4 && (i & 3)) {                                  // short last chunk: flush the partial word
+        const int r = (int)(i & 3);
+        for (int b = 0; b < r; ++b) msg[i - r + b] = (uint8_t)((mword >> (8 * b)) & 1u);
+    }
+}
+
+static int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
+
+}  // namespace txlink
+
+extern "C" int cpb_conv_link_tx(const cpbTrellis *t, const cpbModem *m, int64_t frames, int64_t frame_bits,
+                                uint64_t seed, int64_t first_frame, float noise_sigma, uint8_t *msg_dev, float *y_dev,
+                                void *stream)
+{
+    if (!t || !m || frames < 0 || frame_bits < 1 || first_frame < 0) return CPB_EINVAL;
+    if (frames == 0) return CPB_OK;
+    if (!msg_dev || !y_dev) return CPB_EINVAL;
+    int k, n, S;
+    cpb_trellis_dims(t, &k, &n, &S);
+    if (k != 1 || n < 1 || n > 8) return CPB_EUNSUPPORTED;
+    int mem = 0;
+    while ((1 << mem) < S) ++mem;
+    if ((1 << mem) != S || mem > 24) return CPB_EUNSUPPORTED;
+    const int32_t *nst, *otab;
+    cpb_trellis_host_tables(t, &nst, &otab);
+    txlink::Params p;
+    memset(&p, 0, sizeof(p));
+    // tap masks from the tables (bit 0: input with an empty register; bit b: the state with only delay b set), then
+    // verified on every entry -- a recursive or non-linear trellis is refused (CPB_EUNSUPPORTED)
+    for (int j = 0; j < n; ++j) {
+        uint32_t g = (uint32_t)((otab[0 * 2 + 1] >> (n - 1 - j)) & 1);
+        for (int b = 1; b <= mem; ++b) g |= (uint32_t)((otab[(1 << (mem - b)) * 2 + 0] >> (n - 1 - j)) & 1) << b;
+        p.g[j] = g;
+    }
+    for (int s = 0; s < S; ++s)
+        for (int u = 0; u < 2; ++u) {
+            if (nst[s * 2 + u] != ((u << (mem - 1)) | (s >> 1))) return CPB_EUNSUPPORTED;
+            uint32_t reg = (uint32_t)u;
+            for (int b = 1; b <= mem; ++b) reg |= (uint32_t)((s >> (mem - b)) & 1) << b;
+            int sym = 0;
+            for (int j = 0; j < n; ++j) sym = (sym << 1) | (__builtin_popcount(reg & p.g[j]) & 1);
+            if (sym != otab[s * 2 + u]) return CPB_EUNSUPPORTED;
+        }
+    int Mc, nb;
+    const float *cst;
+    cpb_modem_info(m, &Mc, &nb, &cst);
+    if (nb < 1 || nb > 16) return CPB_EUNSUPPORTED;
+    if ((frame_bits * n) % nb) return CPB_EINVAL;            // the frame must fill whole symbols
+    p.n = n; p.mem = mem; p.nb = nb; p.Mc = Mc;
+    p.frames = frames; p.frame_bits = frame_bits; p.nsym = frame_bits * n / nb;
+    p.first_frame = first_frame;
+    p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
+    p.sigma = noise_sigma;
+    p.spt = 32 * (n / txlink::gcd_int(32 * nb, n));          // even, and spt * nb is a multiple of n
+    p.chunks = ceil_div(p.nsym, (int64_t)p.spt);
+    p.cst = reinterpret_cast<const float2 *>(cst);
+    p.msg = msg_dev;
+    p.y = reinterpret_cast<float2 *>(y_dev);
+    const int64_t threads = frames * p.chunks;
+    const unsigned grid = (unsigned)ceil_div(threads, 128);
+    txlink::conv_link_tx_kernel<<<grid, 128, (size_t)Mc * sizeof(float2), (cudaStream_t)stream>>>(p);
+    CPB_LAUNCH_CHECK();
+    return CPB_OK;
+}

@@ -7,7 +7,8 @@
   (commpy/channels.py:53,74: `noise_std = sqrt((isComplex+1)*nb_tx*Es / (rate*10^(SNR/10)))`, complex noise
   `(N(0,1) + jN(0,1)) * noise_std * 0.5`).  Fading / MIMO channels are out of scope.
 * `ConvLinkGPU` is the batched form for config C5: random bits -> convolutional encoder -> Modem.modulate ->
-  AWGN, all generated on the device with torch, then THIS package's CUDA demapper, Viterbi decoder and error
+  AWGN generated on the device by one CUDA kernel (`conv_link_tx` -> cpb_conv_link_tx, counter-based Philox
+  randomness keyed by the GLOBAL frame index), then this package's demapper, Viterbi decoder and error
   counter; frames shard over ranks and the error counters are all-reduced so every rank takes the same
   stop decision (`links.py:313`).
 """
@@ -19,7 +20,7 @@ import numpy as np
 
 from . import _lib, parallel
 
-__all__ = ["link_performance", "LinkModel", "AwgnSisoChannel", "ConvLinkGPU"]
+__all__ = ["link_performance", "LinkModel", "AwgnSisoChannel", "ConvLinkGPU", "conv_link_tx"]
 
 
 class AwgnSisoChannel:
@@ -202,8 +203,32 @@ def _ff_taps(trellis):
     return taps
 
 
+def conv_link_tx(trellis, modem, frames, frame_bits, seed, first_frame, noise_sigma):
+    """Device-side TX chain of `frames` frames starting at GLOBAL frame index `first_frame`: random message ->
+    conv_encode(..., 'cont') -> modem.modulate -> + noise_sigma * (N(0,1) + jN(0,1)).
+
+    Returns (msg uint8 (frames, frame_bits), y complex64 (frames, frame_bits*n/bits_per_symbol)) as CUDA tensors.
+    The streams depend only on (seed, global frame index): any split of the frames over calls or ranks gives the
+    same frames."""
+    import ctypes as C
+    from .channelcoding.convcode import _trellis_handle
+    torch = _lib.require_cuda()
+    nb = int(modem.num_bits_symbol)
+    if (int(trellis.n) * int(frame_bits)) % nb:
+        raise ValueError("frame_bits * n must be a multiple of the modem's bits per symbol")
+    nsym = int(trellis.n) * int(frame_bits) // nb
+    msg = torch.empty((int(frames), int(frame_bits)), dtype=torch.uint8, device="cuda")
+    y = torch.empty((int(frames), nsym), dtype=torch.complex64, device="cuda")
+    rc = _lib.load().cpb_conv_link_tx(_trellis_handle(trellis), modem._handle(), C.c_int64(int(frames)),
+                                      C.c_int64(int(frame_bits)), C.c_uint64(int(seed) & ((1 << 64) - 1)),
+                                      C.c_int64(int(first_frame)), C.c_float(float(noise_sigma)), _lib.ptr(msg),
+                                      _lib.ptr(y), _lib.stream_ptr(torch))
+    _lib.check(rc, "conv_link_tx")
+    return msg, y
+
+
 class ConvLinkGPU:
-    """Batched convolutional-code link over AWGN on the GPU(s): TX chain in torch, RX chain in this package's CUDA.
+    """Batched convolutional-code link over AWGN on the GPU(s): TX chain and RX chain in this package's CUDA.
 
     Parameters: `trellis` (k=1 feed-forward, e.g. the K=7 (0o133,0o171) code), `modem` (commpy_b200 Modem),
     `frame_bits` information bits per frame ('cont' termination), `frames_per_batch` frames decoded per step and rank.
@@ -224,34 +249,18 @@ class ConvLinkGPU:
         self.rate = Fraction(trellis.k, trellis.n)
 
     # -- TX chain on the device ---------------------------------------------------------------------
-    def _encode(self, msg, torch):
-        M = self.trellis.total_memory
-        n = self.trellis.n
-        pad = torch.nn.functional.pad(msg, (M, 0))
-        coded = torch.empty((msg.shape[0], n * msg.shape[1]), dtype=torch.uint8, device=msg.device)
-        for j in range(n):
-            acc = torch.zeros_like(msg)
-            for b in np.nonzero(self.taps[j])[0]:
-                acc ^= pad[:, M - b:M - b + msg.shape[1]]
-            coded[:, j::n] = acc
-        return coded
+    def noise_std(self, snr_db):
+        """channels.py:74: noise_std = sqrt(2 Es / (rate 10^(SNR/10))); each real component gets noise_std / 2."""
+        return math.sqrt(2 * self.modem.Es / (float(self.rate) * 10 ** (snr_db / 10)))
 
-    def make_batch(self, snr_db, batch_index, torch):
-        """(msg bits, received symbols, noise_var) for one batch of this rank -- everything stays on the device."""
+    def make_batch(self, snr_db, batch_index, torch=None):
+        """(msg bits, received symbols, noise_var) for one batch of this rank -- everything stays on the device.
+        Batch `batch_index` of rank r covers the global frames [(batch_index*world + r) * frames, ... + frames)."""
         rank, world, _ = parallel.world()
-        g = torch.Generator(device="cuda")
-        g.manual_seed(parallel.frame_seed(self.seed, batch_index * max(world, 1) + rank) % (1 << 62))
-        msg = torch.randint(0, 2, (self.frames, self.frame_bits), generator=g, device="cuda", dtype=torch.uint8)
-        coded = self._encode(msg, torch)
-        nb = self.modem.num_bits_symbol
-        w = (1 << torch.arange(nb - 1, -1, -1, device="cuda")).to(torch.int64)
-        idx = (coded.view(self.frames, -1, nb).to(torch.int64) * w).sum(-1)
-        cst = torch.as_tensor(np.asarray(self.modem.constellation, dtype=np.complex64), device="cuda")
-        x = cst[idx]
-        noise_std = math.sqrt(2 * self.modem.Es / (float(self.rate) * 10 ** (snr_db / 10)))       # channels.py:74
-        noise = torch.randn(x.shape + (2,), generator=g, device="cuda", dtype=torch.float32) * (noise_std * 0.5)
-        y = x + torch.view_as_complex(noise)
-        return msg, y, noise_std ** 2                                                              # links.py:329
+        first = (int(batch_index) * max(world, 1) + rank) * self.frames
+        ns = self.noise_std(snr_db)
+        msg, y = conv_link_tx(self.trellis, self.modem, self.frames, self.frame_bits, self.seed, first, 0.5 * ns)
+        return msg, y, ns ** 2                                                                     # links.py:329
 
     # -- RX chain: this package's kernels -------------------------------------------------------------
     def receive_decode_count(self, msg, y, noise_var, counters, torch):

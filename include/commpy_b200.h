@@ -140,6 +140,19 @@ int cpb_demod_hard(const cpbModem *m, const float *y_dev, int64_t n_sym, uint8_t
 int cpb_count_errors(const uint8_t *a_dev, const uint8_t *b_dev, int64_t batch, int64_t L,
                      int64_t lda, int64_t ldb, int64_t *counters_dev, void *stream);
 
+/* ---- transmit side of a coded AWGN link, generated on the device: commpy/links.py:318-329 (per-frame loop of
+ * link_performance: random message, conv_encode 'cont' convcode.py:475-558, Modem.modulate modulation.py:79-98,
+ * AWGN channels.py:181-221) -- the caller of the hot path, so that 1e8-symbol BER points never touch the host. ---- */
+/*
+ * k = 1 feed-forward trellis (else CPB_EUNSUPPORTED), frame_bits information bits per frame ('cont' termination),
+ * frame_bits * n must be a multiple of the modem's bits per symbol.  Counter-based randomness (Philox4x32-10, key =
+ * seed, counter = global frame id = first_frame + local index): the output does not depend on how frames are split
+ * over calls or GPUs.  msg_dev: frames x frame_bits uint8.  y_dev: frames x (frame_bits*n/bits_per_symbol) complex64
+ * = constellation point + noise_sigma * (N(0,1) + j N(0,1)).
+ */
+int cpb_conv_link_tx(const cpbTrellis *t, const cpbModem *m, int64_t frames, int64_t frame_bits, uint64_t seed,
+                     int64_t first_frame, float noise_sigma, uint8_t *msg_dev, float *y_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,3 +109,51 @@ def dvbs2_like_H(seed=3, n=64800, m=32400, n8=12960, n3=19440):
     H.data[:] = 1
     H.sort_indices()
     return H
+
+
+# ---- NumPy model of the device-side TX chain (commpy_b200/csrc/txlink.cu) ------------------------------------------
+def philox4x32_10(ctr, key):
+    """Philox4x32-10 (Salmon et al., Random123).  ctr: (N, 4) uint32 counters, key: (k0, k1).  Returns (N, 4) uint32."""
+    c = np.asarray(ctr, dtype=np.uint64).copy()
+    k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c[:, 0]
+        p1 = np.uint64(0xCD9E8D57) * c[:, 2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & mask
+        hi1, lo1 = p1 >> np.uint64(32), p1 & mask
+        c = np.stack([hi1 ^ c[:, 1] ^ np.uint64(k0), lo1, hi0 ^ c[:, 3] ^ np.uint64(k1), lo0], axis=1)
+        k0 = (k0 + 0x9E3779B9) & 0xFFFFFFFF
+        k1 = (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return c.astype(np.uint32)
+
+
+def conv_link_tx_model(trellis, modem, frames, frame_bits, seed, first_frame, noise_sigma):
+    """(msg, y) exactly as cpb_conv_link_tx defines them (float64 Box-Muller for the noise)."""
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    n, nb = int(trellis.n), int(modem.num_bits_symbol)
+    nsym = n * frame_bits // nb
+    msg = np.zeros((frames, frame_bits), dtype=np.uint8)
+    y = np.zeros((frames, nsym), dtype=np.complex128)
+    cst = np.asarray(modem.constellation)
+    for fl in range(frames):
+        f = first_frame + fl
+        nblk = -(-frame_bits // 128)
+        ctr = np.zeros((nblk, 4), dtype=np.uint64)
+        ctr[:, 0], ctr[:, 1], ctr[:, 2], ctr[:, 3] = f & 0xFFFFFFFF, f >> 32, np.arange(nblk), 0
+        words = philox4x32_10(ctr, key).reshape(-1)                              # 32-bit words, LSB first
+        bits = ((words[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).reshape(-1)[:frame_bits]
+        msg[fl] = bits
+        coded = conv_encode(bits.astype(int), trellis, "cont")
+        idx = coded.reshape(-1, nb).dot(1 << np.arange(nb - 1, -1, -1))
+        npair = -(-nsym // 2)
+        ctr = np.zeros((npair, 4), dtype=np.uint64)
+        ctr[:, 0], ctr[:, 1], ctr[:, 2], ctr[:, 3] = f & 0xFFFFFFFF, f >> 32, np.arange(npair), 1
+        r = philox4x32_10(ctr, key).astype(np.float64)
+        u1a, u2a = r[:, 0] * 2.0 ** -32 + 2.0 ** -33, r[:, 1] * 2.0 ** -32
+        u1b, u2b = r[:, 2] * 2.0 ** -32 + 2.0 ** -33, r[:, 3] * 2.0 ** -32
+        za = np.sqrt(-2 * np.log(u1a)) * np.exp(2j * np.pi * u2a)
+        zb = np.sqrt(-2 * np.log(u1b)) * np.exp(2j * np.pi * u2b)
+        z = np.stack([za, zb], axis=1).reshape(-1)[:nsym]
+        y[fl] = cst[idx] + noise_sigma * z
+    return msg, y

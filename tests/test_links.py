@@ -73,6 +73,53 @@ def test_conv_link_gpu_qpsk_k7_soft_ber_and_oracle_agreement():
     assert int(cnt[0]) == int((dec != msg.cpu().numpy()).sum())
 
 
+def test_philox_model_known_answers():
+    """The NumPy Philox4x32-10 the TX-chain test is built on reproduces the Random123 known-answer vectors."""
+    r = helpers.philox4x32_10(np.array([[0, 0, 0, 0]], dtype=np.uint64), (0, 0))[0]
+    assert [int(x) for x in r] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    r = helpers.philox4x32_10(np.array([[0xffffffff] * 4], dtype=np.uint64), (0xffffffff, 0xffffffff))[0]
+    assert [int(x) for x in r] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    r = helpers.philox4x32_10(np.array([[0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344]], dtype=np.uint64),
+                              (0xa4093822, 0x299f31d0))[0]
+    assert [int(x) for x in r] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("modem_m,frame_bits", [(4, 200), (16, 1024), (64, 300), (256, 4096)])
+def test_conv_link_tx_kernel_matches_numpy_model(modem_m, frame_bits):
+    """cpb_conv_link_tx: message bits and noiseless symbols bit-exact against conv_encode + Modem.modulate on the
+    Philox message stream, noise equal to the float64 Box-Muller model to fast-math accuracy, and the frames do not
+    depend on how they are split over calls (first_frame) -- the multi-GPU sharding contract."""
+    import torch
+    from commpy_b200.links import conv_link_tx
+    from commpy_b200.modulation import QAMModem
+    tr = helpers.k7()
+    modem = QAMModem(modem_m)
+    frames, seed, first = 5, 0x1234567890abcdef, (1 << 33) + 7
+    want_msg, want_y0 = helpers.conv_link_tx_model(tr, modem, frames, frame_bits, seed, first, 0.0)
+    msg, y0 = conv_link_tx(tr, modem, frames, frame_bits, seed, first, 0.0)
+    assert np.array_equal(msg.cpu().numpy(), want_msg)
+    assert np.array_equal(y0.cpu().numpy(), want_y0.astype(np.complex64))
+    _, want_y = helpers.conv_link_tx_model(tr, modem, frames, frame_bits, seed, first, 0.75)
+    msg2, y = conv_link_tx(tr, modem, frames, frame_bits, seed, first, 0.75)
+    assert torch.equal(msg, msg2)
+    assert np.abs(y.cpu().numpy() - want_y).max() < 2e-3
+    # split invariance: frames [first+2, first+5) generated on their own are the same frames
+    msg3, y3 = conv_link_tx(tr, modem, 3, frame_bits, seed, first + 2, 0.75)
+    assert torch.equal(msg3, msg[2:]) and torch.equal(y3, y[2:])
+    # noise statistics over a larger batch: unit variance per component, zero mean, uncorrelated I/Q
+    _, yb = conv_link_tx(tr, modem, 256, frame_bits, 7, 0, 1.0)
+    _, yc = conv_link_tx(tr, modem, 256, frame_bits, 7, 0, 0.0)
+    z = (yb - yc).cpu().numpy().reshape(-1)
+    nz = z.size
+    assert abs(z.real.mean()) < 5 / math.sqrt(nz) and abs(z.imag.mean()) < 5 / math.sqrt(nz)
+    assert abs(z.real.var() - 1) < 8 / math.sqrt(nz) and abs(z.imag.var() - 1) < 8 / math.sqrt(nz)
+    assert abs((z.real * z.imag).mean()) < 5 / math.sqrt(nz)
+    # recursive trellises are refused (no tap form)
+    with pytest.raises(NotImplementedError):
+        conv_link_tx(helpers.rsc_k4(), QAMModem(4), 2, 64, 1, 0, 0.1)
+
+
 @pytest.mark.gpu
 def test_dropin_linkmodel_with_gpu_receiver_and_decoder():
     """commpy/examples/conv_encode_decode.py:99-127 shape: QPSK, (5,7) code, hard and unquantized Viterbi via LinkModel."""
