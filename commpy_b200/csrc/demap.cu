@@ -46,44 +46,55 @@ constexpr float TINY = 7.8886e-31f;     // 2^-100
 // raw MUFU.EX2 (ex2a() adds range handling for denormal results that the sums below do not need)
 __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// one axis of a separable constellation: R levels, HB = log2(R) bits; out[h] = LLR of axis bit h (LSB = 0)
+// one axis of a separable constellation: R levels, HB = log2(R) bits; out[h] = LLR of axis bit h (LSB = 0).
+// lev[i] is the level of axis label i.  Per level: y - lev, square, one FMA against the nearest level's distance,
+// one MUFU.EX2.  The 2*HB group sums share a binary tree over the label bits (R-2 + 2(R-HB-1) adds instead of
+// HB*R): s_l[j] = sum of the 2^l labels j*2^l .. (j+1)*2^l-1, and bit h splits level h into odd / even j.
 template <int HB>
-__device__ __forceinline__ void axis_llr(float y, const float *__restrict__ lev, float inv_nv_log2e, float (&out)[HB])
+__device__ __forceinline__ void axis_llr(float y, const float (&lev)[64], float inv_nv_log2e, float (&out)[HB])
 {
     constexpr int R = 1 << HB;
-    float d[R];
-    float dmin = 3.0e38f;
+    float tt[R];
+    float tmin = 3.0e38f;
 #pragma unroll
     for (int i = 0; i < R; ++i) {
         const float t = y - lev[i];
-        d[i] = t * t * inv_nv_log2e;
-        dmin = fminf(dmin, d[i]);
+        tt[i] = t * t;
+        tmin = fminf(tmin, tt[i]);
     }
+    const float dmin = tmin * inv_nv_log2e;
+    float s[R];                                     // in-place tree: after level l, s[j << l] holds s_l[j]
+#pragma unroll
+    for (int i = 0; i < R; ++i) s[i] = ex2a(fmaf(tt[i], -inv_nv_log2e, dmin));
     float num[HB], den[HB];
 #pragma unroll
-    for (int h = 0; h < HB; ++h) { num[h] = 0.0f; den[h] = 0.0f; }
+    for (int h = 0; h < HB; ++h) {
+        const int step = 1 << h;                    // entries of level h sit at multiples of step
+        float n = s[step], d = s[0];
 #pragma unroll
-    for (int i = 0; i < R; ++i) {
-        const float e = ex2a(dmin - d[i]);
+        for (int j = 2; j < (R >> h); j += 2) { d += s[j * step]; n += s[(j + 1) * step]; }
+        num[h] = n; den[h] = d;
+        if (h + 1 < HB) {
 #pragma unroll
-        for (int h = 0; h < HB; ++h) {
-            if ((i >> h) & 1) num[h] += e; else den[h] += e;
+            for (int j = 0; j < (R >> h); j += 2) s[j * step] += s[(j + 1) * step];
         }
     }
 #pragma unroll
     for (int h = 0; h < HB; ++h) {
         float l1 = __log2f(num[h]), l0 = __log2f(den[h]);
         if (fminf(num[h], den[h]) < TINY) {
+            // a whole group underflowed against the global nearest level: redo it against its own nearest level
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
                 if ((g ? num[h] : den[h]) >= TINY) continue;
-                float dg = 3.0e38f, sg = 0.0f;
+                float tg = 3.0e38f, sg = 0.0f;
 #pragma unroll
                 for (int i = 0; i < R; ++i)
-                    if (((i >> h) & 1) == g) dg = fminf(dg, d[i]);
+                    if (((i >> h) & 1) == g) tg = fminf(tg, tt[i]);
+                const float dg = tg * inv_nv_log2e;
 #pragma unroll
                 for (int i = 0; i < R; ++i)
-                    if (((i >> h) & 1) == g) sg += ex2a(dg - d[i]);
+                    if (((i >> h) & 1) == g) sg += ex2a(fmaf(tt[i], -inv_nv_log2e, dg));
                 const float l = (dmin - dg) + __log2f(sg);
                 if (g) l1 = l; else l0 = l;
             }
@@ -97,15 +108,13 @@ __global__ void __launch_bounds__(256) demod_soft_separable(const float2 *__rest
                                                             const SepTables tab, float inv_nv_log2e,
                                                             float *__restrict__ llr)
 {
-    __shared__ float lev_i[1 << HB], lev_q[1 << HB];
-    if (threadIdx.x < (1 << HB)) { lev_i[threadIdx.x] = tab.pi[threadIdx.x]; lev_q[threadIdx.x] = tab.pq[threadIdx.x]; }
-    __syncthreads();
+    // the levels are read straight from the kernel parameters (constant bank operands of the FADDs)
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nsym) return;
     const float2 v = __ldg(&y[i]);
     float li[HB], lq[HB];
-    axis_llr<HB>(v.x, lev_i, inv_nv_log2e, li);     // high half of the index bits
-    axis_llr<HB>(v.y, lev_q, inv_nv_log2e, lq);     // low half
+    axis_llr<HB>(v.x, tab.pi, inv_nv_log2e, li);     // high half of the index bits
+    axis_llr<HB>(v.y, tab.pq, inv_nv_log2e, lq);     // low half
     // output position nb-1-b for bit b (modulation.py:137): MSB first = axis I bits (high) then axis Q bits
     float o[2 * HB];
 #pragma unroll

@@ -27,5 +27,9 @@ if which in ("all", "turbo"):
     s2 = 1.0 / (2 * (1 / 3) * 10 ** (1.0 / 10))
     ys, y1, y2 = ((-1 + s2 ** 0.5 * torch.randn(batch, N, device="cuda")).float() for _ in range(3))
     turbo_decode_batch(ys, y1, y2, tr, s2, 1, il)
+if which in ("all", "tx"):
+    from commpy_b200.links import conv_link_tx
+    for _ in range(2):
+        conv_link_tx(helpers.k7(), QAMModem(256), 8192, 4096, 4, 0, 0.5)
 torch.cuda.synchronize()
 print("done")
