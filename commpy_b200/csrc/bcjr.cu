@@ -16,6 +16,8 @@
 // exactly like the reference.
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 using namespace cpb;
@@ -726,15 +728,19 @@ static int nwindows(int N) { return (N > WIN + WIN / 2) ? (int)ceil_div(N, WIN) 
 template <class T>
 static int launch(const Params &p, bool vec, cudaStream_t st)
 {
-    const unsigned grid = (unsigned)ceil_div(p.NT, 128);
+    unsigned grid = (unsigned)ceil_div(p.NT, 128);
     if (vec && (p.win % CK) == 0) {
-        const size_t smem = sizeof(float) * CK * (T::S + 3) * 128;
+        // one warp per CTA: 49,152 threads (C3: 8,192 frames x 6 windows) are 1,536 CTAs instead of 384, which
+        // spreads evenly over 148 SMs (measured 0.88 vs 0.91 ms per pass)
+        const int bd = 32;
+        grid = (unsigned)ceil_div(p.NT, bd);
+        const size_t smem = sizeof(float) * CK * (T::S + 3) * bd;
 #ifdef CPB_BCJR_LOGDOMAIN
         CPB_CUDA(cudaFuncSetAttribute(map_ckpt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         map_ckpt_kernel<T><<<grid, 128, smem, st>>>(p);
 #else
         CPB_CUDA(cudaFuncSetAttribute(map_lin_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        map_lin_kernel<T><<<grid, 128, smem, st>>>(p);
+        map_lin_kernel<T><<<grid, bd, smem, st>>>(p);
 #endif
     } else if (vec) map_tpf_kernel<T, 4><<<grid, 128, 0, st>>>(p);
     else map_tpf_kernel<T, 1><<<grid, 128, 0, st>>>(p);
