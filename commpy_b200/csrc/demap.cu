@@ -7,7 +7,8 @@
 // raw exponentials and so returns +-inf/NaN once they underflow; here the smallest exponent is subtracted
 // first, which is the same number wherever the reference is finite.
 //
-// Two kernels, one thread per symbol (coalesced 8-byte loads, 16-byte LLR stores):
+// Two kernels, one thread per symbol (coalesced 8-byte loads, 16-byte LLR stores; the separable kernel reads its
+// axis levels as constant-bank operands, the general one from a shared-memory copy of the constellation):
 //   demod_soft_separable  Gray-labelled square QAM, c[k] = pamI[k_hi] + j*pamQ[k_lo] (modulation.py:242-262
 //                         + the Gray reorder of :68-77): the sums factor per axis, 2*sqrt(M) exponentials
 //                         instead of M*log2(M) (32 instead of 2048 at 256-QAM).

@@ -12,9 +12,10 @@
 //   variable pass (one thread per variable x frame group): tot_j = sum_i R_ij in ascending check index
 //        (the reference's summation order), post_j = tot_j + llr_j.  Frames whose syndrome was already zero
 //        are frozen here: their posteriors stay those of the previous iteration, exactly the reference's break.
-// Layout: frames are the innermost dimension of every array ([edge][frame], [variable][frame]), so each
+// Layout: frames are the innermost dimension of every array ([chunk][edge][frame], [variable][frame]), so each
 // access is a coalesced 16-byte vector (float4 = 4 frames, double2 = 2 frames) whatever the edge index,
-// and the CSR/CSC index reads are warp-uniform.  Algorithmic HBM traffic per frame-iteration: 12*E + 8*n bytes
+// and the CSR/CSC index reads are warp-uniform.  For batches of >= 128 frames the min-sum check pass is
+// bulk::cn_bulk_kernel, which stages whole rows through shared memory with the bulk-copy engine (see below).  Algorithmic HBM traffic per frame-iteration: 12*E + 8*n bytes
 // in fp32 (read R + write R in the check pass, read R in the variable pass, read llr + write post).
 //
 // CPB_LDPC_FP64 runs the same kernels in double: min-sum is only abs/min/negate/add/sub, the adds happen in
@@ -40,19 +41,6 @@ namespace ldpc {
 template <typename T> struct VecOf;
 template <> struct VecOf<float> { static constexpr int V = 4; struct alignas(16) type { float v[4]; }; };
 template <> struct VecOf<double> { static constexpr int V = 2; struct alignas(16) type { double v[2]; }; };
-
-// 16-byte global load that the compiler will not move (asm volatile keeps program order among such loads)
-template <typename VT>
-__device__ __forceinline__ VT ld16(const void *p)
-{
-    static_assert(sizeof(VT) == 16, "16-byte vector expected");
-    uint32_t a, b, c, d;
-    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
-    VT v;
-    uint32_t *w = reinterpret_cast<uint32_t *>(&v);
-    w[0] = a; w[1] = b; w[2] = c; w[3] = d;
-    return v;
-}
 
 // R (check-to-variable messages) is stored chunk-major: [frame chunk][edge][RS frames], RS = frames per chunk
 // (RS = F, one chunk, unless the bulk-copy check pass is in use), so that the rows of one check node and one
