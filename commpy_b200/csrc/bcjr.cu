@@ -610,13 +610,19 @@ __global__ void __launch_bounds__(128) map_lin_kernel(const Params p)
         const int tb = min(N, hi + WARM);
 #pragma unroll
         for (int s = 0; s < S; ++s) B[s] = 1.0f / S;                      // beta_N = 1 for all states (:225-226), scale free
-        float ns_[G], np_[G], nl_[G];
+        // inputs are fetched two groups (8 steps) ahead of their use: with ~10 warps per SM a DRAM round trip is longer
+        // than one group of beta steps
+        float ns_[G], np_[G], nl_[G], ms_[G], mp_[G], ml_[G];
         ld4(fs, tb - G, ns_); ld4(fp, tb - G, np_); ld4(fl, tb - G, nl_);
+        if (tb - G > lo) { ld4(fs, tb - 2 * G, ms_); ld4(fp, tb - 2 * G, mp_); ld4(fl, tb - 2 * G, ml_); }
         for (int e1 = tb; e1 > lo; e1 -= G) {
             float vs[G], vp[G], vl[G];
 #pragma unroll
-            for (int i = 0; i < G; ++i) { vs[i] = ns_[i]; vp[i] = np_[i]; vl[i] = nl_[i]; }
-            if (e1 - G > lo) { ld4(fs, e1 - 2 * G, ns_); ld4(fp, e1 - 2 * G, np_); ld4(fl, e1 - 2 * G, nl_); }
+            for (int i = 0; i < G; ++i) {
+                vs[i] = ns_[i]; vp[i] = np_[i]; vl[i] = nl_[i];
+                ns_[i] = ms_[i]; np_[i] = mp_[i]; nl_[i] = ml_[i];
+            }
+            if (e1 - 2 * G > lo) { ld4(fs, e1 - 3 * G, ms_); ld4(fp, e1 - 3 * G, mp_); ld4(fl, e1 - 3 * G, ml_); }
 #pragma unroll
             for (int i = G - 1; i >= 0; --i) {
                 const int t = e1 - (G - 1 - i);
@@ -666,21 +672,35 @@ __global__ void __launch_bounds__(128) map_lin_kernel(const Params p)
 #pragma unroll
         for (int i = 0; i < G; ++i) alpha_step(vs[i], vp[i], vl[i], nullptr, false, dummy);
     }
+    // the inputs and the beta checkpoint of a segment are fetched while the previous segment is being processed
+    static_assert(CK == 2 * G, "segment = two vector groups");
+    float xin[2][3][G], xck[S];
+    auto fetch_segment = [&](int s0, int j) {
+        const int ns = min(CK, hi - s0);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (h * G < ns) { ld4(fs, s0 + h * G, xin[h][0]); ld4(fp, s0 + h * G, xin[h][1]); ld4(fl, s0 + h * G, xin[h][2]); }
+#pragma unroll
+        for (int s = 0; s < S; ++s) xck[s] = ck[((int64_t)j * S + s) * p.NT];
+    };
+    if (lo < hi) fetch_segment(lo, 0);
     for (int s0 = lo, j = 0; s0 < hi; s0 += CK, ++j) {
         const int ns = min(CK, hi - s0);                        // a multiple of 4
-        for (int q = 0; q < ns; q += G) {
-            float vs[G], vp[G], vl[G];
-            ld4(fs, s0 + q, vs); ld4(fp, s0 + q, vp); ld4(fl, s0 + q, vl);
 #pragma unroll
-            for (int i = 0; i < G; ++i) {
-                si[((q + i) * 3 + 0) * bd + tid] = vs[i];
-                si[((q + i) * 3 + 1) * bd + tid] = vp[i];
-                si[((q + i) * 3 + 2) * bd + tid] = vl[i];
+        for (int h = 0; h < 2; ++h) {
+            if (h * G < ns) {
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    si[((h * G + i) * 3 + 0) * bd + tid] = xin[h][0][i];
+                    si[((h * G + i) * 3 + 1) * bd + tid] = xin[h][1][i];
+                    si[((h * G + i) * 3 + 2) * bd + tid] = xin[h][2][i];
+                }
             }
         }
         float B[S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) B[s] = ck[((int64_t)j * S + s) * p.NT];
+        for (int s = 0; s < S; ++s) B[s] = xck[s];
+        if (s0 + CK < hi) fetch_segment(s0 + CK, j + 1);
         for (int i = ns - 1; i >= 0; --i) {
 #pragma unroll
             for (int s = 0; s < S; ++s) sb[(i * S + s) * bd + tid] = B[s];          // beta_{s0+1+i}
