@@ -198,6 +198,7 @@ struct Params {
     int64_t NT;
     float *L_out;
     uint8_t *bits_out;
+    int ext;                     // map_lin_kernel only: L_out receives L - La (the extrinsic turbo_decode forms, turbo.py:318,328)
 };
 
 template <class T, int G>     // G = steps per vector access (4: float4 / uchar4, 1: scalar)
@@ -715,7 +716,12 @@ __global__ void __launch_bounds__(128) map_lin_kernel(const Params p)
                            sb + (k * S) * bd + tid, true, Lv[i]);
             }
             const int e0 = s0 + q;
-            *reinterpret_cast<float4 *>(p.L_out + f * N + e0) = make_float4(Lv[0], Lv[1], Lv[2], Lv[3]);
+            if (p.ext)
+                *reinterpret_cast<float4 *>(p.L_out + f * N + e0) =
+                    make_float4(Lv[0] - si[((q + 0) * 3 + 2) * bd + tid], Lv[1] - si[((q + 1) * 3 + 2) * bd + tid],
+                                Lv[2] - si[((q + 2) * 3 + 2) * bd + tid], Lv[3] - si[((q + 3) * 3 + 2) * bd + tid]);
+            else
+                *reinterpret_cast<float4 *>(p.L_out + f * N + e0) = make_float4(Lv[0], Lv[1], Lv[2], Lv[3]);
             if (p.bits_out) {
                 uchar4 b;
                 b.x = (p.mode == 1 && Lv[0] > 0.0f); b.y = (p.mode == 1 && Lv[1] > 0.0f);
@@ -757,7 +763,7 @@ static int launch(const Params &p, bool vec, cudaStream_t st)
         const size_t smem = sizeof(float) * CK * (T::S + 3) * bd;
 #ifdef CPB_BCJR_LOGDOMAIN
         CPB_CUDA(cudaFuncSetAttribute(map_ckpt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        map_ckpt_kernel<T><<<grid, 128, smem, st>>>(p);
+        map_ckpt_kernel<T><<<grid, bd, smem, st>>>(p);
 #else
         CPB_CUDA(cudaFuncSetAttribute(map_lin_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         map_lin_kernel<T><<<grid, bd, smem, st>>>(p);
@@ -794,7 +800,7 @@ __global__ void __launch_bounds__(256) scatter_sub_kernel(const float *__restric
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
         const int64_t f = g / N;
         const int i = (int)(g - f * N);
-        out[f * N + __ldg(&perm[i])] = a[g] - b[g];
+        out[f * N + __ldg(&perm[i])] = a[g] - (b ? b[g] : 0.0f);
     }
 }
 
@@ -806,6 +812,26 @@ __global__ void __launch_bounds__(256) row_gather_sub_kernel(const float *__rest
 {
     extern __shared__ float row[];
     const int64_t base = (int64_t)blockIdx.x * N;
+    const bool v4 = ((N & 3) == 0) && ((((uintptr_t)(a + base)) | ((uintptr_t)(out + base)) | ((uintptr_t)perm) |
+                                        (b ? (uintptr_t)(b + base) : 0)) & 15) == 0;
+    if (v4) {                                                  // 16-byte global accesses, 4-byte shared-memory gathers
+        const float4 *a4 = reinterpret_cast<const float4 *>(a + base);
+        const float4 *b4 = b ? reinterpret_cast<const float4 *>(b + base) : nullptr;
+        float4 *r4 = reinterpret_cast<float4 *>(row);
+        for (int i = threadIdx.x; i < (N >> 2); i += blockDim.x) {
+            float4 v = a4[i];
+            if (b4) { const float4 w = b4[i]; v.x -= w.x; v.y -= w.y; v.z -= w.z; v.w -= w.w; }
+            r4[i] = v;
+        }
+        __syncthreads();
+        const int4 *p4 = reinterpret_cast<const int4 *>(perm);
+        float4 *o4 = reinterpret_cast<float4 *>(out + base);
+        for (int i = threadIdx.x; i < (N >> 2); i += blockDim.x) {
+            const int4 q = __ldg(&p4[i]);
+            o4[i] = make_float4(row[q.x], row[q.y], row[q.z], row[q.w]);
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < N; i += blockDim.x) row[i] = a[base + i] - (b ? b[base + i] : 0.0f);
     __syncthreads();
     for (int i = threadIdx.x; i < N; i += blockDim.x) out[base + i] = row[__ldg(&perm[i])];
@@ -816,7 +842,25 @@ __global__ void __launch_bounds__(256) row_scatter_sub_kernel(const float *__res
 {
     extern __shared__ float row[];
     const int64_t base = (int64_t)blockIdx.x * N;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) row[__ldg(&perm[i])] = a[base + i] - b[base + i];
+    const bool v4 = ((N & 3) == 0) && ((((uintptr_t)(a + base)) | ((uintptr_t)(out + base)) | ((uintptr_t)perm) |
+                                        (b ? (uintptr_t)(b + base) : 0)) & 15) == 0;
+    if (v4) {
+        const float4 *a4 = reinterpret_cast<const float4 *>(a + base);
+        const float4 *b4 = b ? reinterpret_cast<const float4 *>(b + base) : nullptr;
+        const int4 *p4 = reinterpret_cast<const int4 *>(perm);
+        for (int i = threadIdx.x; i < (N >> 2); i += blockDim.x) {
+            float4 v = a4[i];
+            if (b4) { const float4 w = b4[i]; v.x -= w.x; v.y -= w.y; v.z -= w.z; v.w -= w.w; }
+            const int4 q = __ldg(&p4[i]);
+            row[q.x] = v.x; row[q.y] = v.y; row[q.z] = v.z; row[q.w] = v.w;
+        }
+        __syncthreads();
+        const float4 *r4 = reinterpret_cast<const float4 *>(row);
+        float4 *o4 = reinterpret_cast<float4 *>(out + base);
+        for (int i = threadIdx.x; i < (N >> 2); i += blockDim.x) o4[i] = r4[i];
+        return;
+    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) row[__ldg(&perm[i])] = a[base + i] - (b ? b[base + i] : 0.0f);
     __syncthreads();
     for (int i = threadIdx.x; i < N; i += blockDim.x) out[base + i] = row[i];
 }
@@ -854,7 +898,8 @@ static size_t beta_floats(int64_t frames, int N, int S)
 }
 
 static int launch_map(const cpbTrellis *t, int S, const float *sys, const float *par, const float *La, int64_t batch,
-                      int N, float noise_var, int mode, float *beta, float *L_out, uint8_t *bits, cudaStream_t st)
+                      int N, float noise_var, int mode, float *beta, float *L_out, uint8_t *bits, cudaStream_t st,
+                      int want_ext = 0, int *did_ext = nullptr)
 {
     const int32_t *hn = nullptr, *ho = nullptr;
     cpb_trellis_host_tables(t, &hn, &ho);
@@ -866,6 +911,11 @@ static int launch_map(const cpbTrellis *t, int S, const float *sys, const float 
         p.L_out = L_out; p.bits_out = bits;
         const bool vec = (N % 4 == 0) && ((((uintptr_t)sys | (uintptr_t)par | (uintptr_t)La | (uintptr_t)L_out) & 15) == 0) &&
                          (bits == nullptr || (((uintptr_t)bits) & 3) == 0);
+        p.ext = 0;
+#ifndef CPB_BCJR_LOGDOMAIN
+        if (want_ext && vec && (p.win % tpf::CK) == 0) p.ext = 1;
+#endif
+        if (did_ext) *did_ext = p.ext;
         if (tpf::matches<tpf::RscK4>(hn, ho, S)) return tpf::launch<tpf::RscK4>(p, vec, st);
         if (tpf::matches<tpf::RscK4Legacy>(hn, ho, S)) return tpf::launch<tpf::RscK4Legacy>(p, vec, st);
         if (tpf::matches<tpf::RscK3Legacy>(hn, ho, S)) return tpf::launch<tpf::RscK3Legacy>(p, vec, st);
@@ -873,6 +923,7 @@ static int launch_map(const cpbTrellis *t, int S, const float *sys, const float 
         if (tpf::matches<tpf::RscK3>(hn, ho, S)) return tpf::launch<tpf::RscK3>(p, vec, st);
     }
     // any other rate-1/2 trellis with 2..32 states: table-driven lane-per-state kernel
+    if (did_ext) *did_ext = 0;
     const int32_t *nx = cpb_trellis_next_dev(t), *ot = cpb_trellis_out_dev(t), *pd = cpb_trellis_pred_dev(t);
     const float inv2s2 = 1.0f / (2.0f * noise_var);
     const int fpw = 32 / S;
@@ -976,15 +1027,18 @@ int cpb_turbo_decode(const cpbTrellis *t, const float *sys_dev, const float *par
         if (rows) bcjr::row_gather_sub_kernel<<<(unsigned)nb, 256, rsm, st>>>(sy, nullptr, perm_dev, (int)N, sys_i);
         else bcjr::gather_sub_kernel<<<eg, 256, 0, st>>>(sy, nullptr, perm_dev, nb, (int)N, sys_i);          // :310
         for (int it = 0; it < n_iter && rc == CPB_OK; ++it) {
-            rc = bcjr::launch_map(t, S, sy, p1, La1, nb, (int)N, noise_variance, 0, beta, L1, nullptr, st);   // :315
+            // when the probability-domain kernel runs it writes L - L_int itself (did = 1) and the permutation kernels
+            // read one array instead of two
+            int did = 0;
+            rc = bcjr::launch_map(t, S, sy, p1, La1, nb, (int)N, noise_variance, 0, beta, L1, nullptr, st, 1, &did);   // :315
             if (rc) break;
-            if (rows) bcjr::row_gather_sub_kernel<<<(unsigned)nb, 256, rsm, st>>>(L1, La1, perm_dev, (int)N, La2);
-            else bcjr::gather_sub_kernel<<<eg, 256, 0, st>>>(L1, La1, perm_dev, nb, (int)N, La2);            // :318-319
+            if (rows) bcjr::row_gather_sub_kernel<<<(unsigned)nb, 256, rsm, st>>>(L1, did ? nullptr : La1, perm_dev, (int)N, La2);
+            else bcjr::gather_sub_kernel<<<eg, 256, 0, st>>>(L1, did ? nullptr : La1, perm_dev, nb, (int)N, La2);   // :318-319
             const int mode = (it == n_iter - 1) ? 1 : 0;                                                // :320-323
-            rc = bcjr::launch_map(t, S, sys_i, p2, La2, nb, (int)N, noise_variance, mode, beta, L2, dec, st);  // :326
+            rc = bcjr::launch_map(t, S, sys_i, p2, La2, nb, (int)N, noise_variance, mode, beta, L2, dec, st, 1, &did);  // :326
             if (rc) break;
-            if (rows) bcjr::row_scatter_sub_kernel<<<(unsigned)nb, 256, rsm, st>>>(L2, La2, perm_dev, (int)N, La1);
-            else bcjr::scatter_sub_kernel<<<eg, 256, 0, st>>>(L2, La2, perm_dev, nb, (int)N, La1);           // :328-329
+            if (rows) bcjr::row_scatter_sub_kernel<<<(unsigned)nb, 256, rsm, st>>>(L2, did ? nullptr : La2, perm_dev, (int)N, La1);
+            else bcjr::scatter_sub_kernel<<<eg, 256, 0, st>>>(L2, did ? nullptr : La2, perm_dev, nb, (int)N, La1);   // :328-329
         }
         if (rc) break;
         if (rows) bcjr::row_scatter_bits_kernel<<<(unsigned)nb, 256, (size_t)N, st>>>(dec, perm_dev, (int)N, bits_out_dev + f0 * N);
