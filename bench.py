@@ -479,6 +479,7 @@ def run_extras(torch):
         # the whole BER point of config 5 through the public API: TX kernel (cpb_conv_link_tx) + RX chain + stop rule,
         # 2 batches of 49,152 frames = 1.0e8 symbols at Eb/N0 = 14 dB
         ms_tx = timeit(lambda: link.make_batch(snr, 1, torch), reps=3, warm=1)
+        link.link_performance([snr], send_max=1, err_min=10 ** 12)       # warm-up: one batch (allocator, handles)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         send_max = 2 * 49152 * 4096
