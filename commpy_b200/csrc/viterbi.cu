@@ -257,8 +257,8 @@ struct Walker {
 constexpr int TASK_CAP = 384;      // retired paths kept per block and warp; beyond that they are finished inline
 
 template <class CODE, int PACK, bool FINAL>
-__device__ __noinline__ void tb_block(const Smem<PACK> sm, int ts, int te, int slot_te, int D, int L,
-                                      uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec16)
+__device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int te, int slot_te, int D, int L,
+                                               uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec16)
 {
     using PT = typename std::conditional<FINAL, unsigned long long, uint32_t>::type;
     constexpr int M = CODE::M;
@@ -384,6 +384,25 @@ __device__ __noinline__ void tb_block(const Smem<PACK> sm, int ts, int te, int s
         }
     }
     __syncwarp();
+}
+
+// the traceback is a call in the hard kernel (its 64 packed keys stay in callee-saved registers) and inlined in the
+// register-capped soft kernel (CPB_TB_INLINE_SOFT)
+template <class CODE, int PACK, bool FINAL>
+__device__ __noinline__ void tb_block_call(const Smem<PACK> sm, int ts, int te, int slot_te, int D, int L,
+                                           uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec16)
+{
+    tb_block_body<CODE, PACK, FINAL>(sm, ts, te, slot_te, D, L, out0, out1, valid_mask, out_vec16);
+}
+#ifndef CPB_TB_INLINE_SOFT
+#define CPB_TB_INLINE_SOFT 1
+#endif
+template <class CODE, int PACK, bool FINAL>
+__device__ __forceinline__ void tb_block(const Smem<PACK> sm, int ts, int te, int slot_te, int D, int L,
+                                         uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec16)
+{
+    if (PACK == 1 && CPB_TB_INLINE_SOFT) tb_block_body<CODE, PACK, FINAL>(sm, ts, te, slot_te, D, L, out0, out1, valid_mask, out_vec16);
+    else tb_block_call<CODE, PACK, FINAL>(sm, ts, te, slot_te, D, L, out0, out1, valid_mask, out_vec16);
 }
 
 template <class CODE, int PACK, int QD = 4>
