@@ -629,9 +629,9 @@ static int run(const cpbLdpc *h, T *llr, int64_t batch, int n_iters, int spa, ui
         const unsigned cn_blocks = (unsigned)ceil_div((int64_t)h->m * G, 256);
         const unsigned vn_blocks = (unsigned)ceil_div((int64_t)h->n * G, 256);
         // bulk-copy staged check pass: min-sum, row degree <= 32, frame chunks of 256 or 128
+        // (CPB_LDPC_NO_BULK=1 forces the register-staged kernels: used by the test that compares the two paths)
         bool use_bulk = !spa && h->max_row_deg <= bulk::MAXDEG && !getenv("CPB_LDPC_NO_BULK");
         int FT = (F % 256 == 0) ? 256 : ((F % 128 == 0) ? 128 : 0);
-        { const char *e_ft = getenv("CPB_LDPC_FT"); if (e_ft && F % atoi(e_ft) == 0) FT = atoi(e_ft); }
         int nchunks = 0, bulk_grid = 0;
         size_t bulk_smem = 0;
         if (FT == 0) use_bulk = false;
