@@ -257,7 +257,7 @@ class ConvLinkGPU:
         """(msg bits, received symbols, noise_var) for one batch of this rank -- everything stays on the device.
         Batch `batch_index` of rank r covers the global frames [(batch_index*world + r) * frames, ... + frames)."""
         rank, world, _ = parallel.world()
-        first = (int(batch_index) * max(world, 1) + rank) * self.frames
+        first = parallel.batch_first_frame(batch_index, self.frames, rank, max(world, 1))
         ns = self.noise_std(snr_db)
         msg, y = conv_link_tx(self.trellis, self.modem, self.frames, self.frame_bits, self.seed, first, 0.5 * ns)
         return msg, y, ns ** 2                                                                     # links.py:329

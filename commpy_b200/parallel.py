@@ -29,6 +29,15 @@ def frame_seed(seed, frame_index):
     return (int(seed) * 0x9E3779B97F4A7C15 + int(frame_index) * 0xBF58476D1CE4E5B9) % (1 << 63)
 
 
+def batch_first_frame(batch_index, frames_per_batch, rank, world_size):
+    """GLOBAL index of the first frame of batch `batch_index` on rank `rank` when every rank generates
+    `frames_per_batch` frames per step: step b covers the frames [b*W*F, (b+1)*W*F), rank r the r-th slice of it.
+    The frame streams are keyed by this index (cpb_conv_link_tx), so a BER point sees the same frames for any W."""
+    if world_size < 1 or not (0 <= rank < world_size) or batch_index < 0 or frames_per_batch < 0:
+        raise ValueError("bad batch request")
+    return (int(batch_index) * int(world_size) + int(rank)) * int(frames_per_batch)
+
+
 def allreduce_counters(counters, group=None):
     """Sum an int64 counter tensor over all ranks (no-op for a single process).  Returns the tensor."""
     import torch.distributed as dist

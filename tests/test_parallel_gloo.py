@@ -65,3 +65,32 @@ def test_counters_allreduce_world2_matches_single_process():
     for rank, c, keep in res:
         assert c == want, (rank, c, want)          # identical global counters on every rank, independent of world size
         assert keep is False
+
+
+def test_batch_first_frame_tiles_the_frame_axis(monkeypatch):
+    """Each step of W ranks x F frames covers a contiguous block of global frame indices exactly once, so the frames of
+    a BER point (keyed by global index in cpb_conv_link_tx) do not depend on the number of ranks."""
+    from commpy_b200 import parallel
+    F = 7
+    for W in (1, 2, 4, 8):
+        seen = []
+        for b in range(3):
+            for r in range(W):
+                first = parallel.batch_first_frame(b, F, r, W)
+                seen.extend(range(first, first + F))
+        assert seen == list(range(3 * W * F))
+    # the same 8 x 7 frames, generated as one step of 8 ranks or as four steps of 2 ranks
+    a = sorted(f for r in range(8) for f in range(parallel.batch_first_frame(0, F, r, 8), parallel.batch_first_frame(0, F, r, 8) + F))
+    b = sorted(f for s_ in range(4) for r in range(2)
+               for f in range(parallel.batch_first_frame(s_, F, r, 2), parallel.batch_first_frame(s_, F, r, 2) + F))
+    assert a == b
+    # ConvLinkGPU.make_batch asks the TX kernel for exactly that index (no GPU needed: the kernel call is stubbed)
+    import commpy_b200.links as links
+    from commpy_b200.modulation import QAMModem
+    import helpers
+    calls = []
+    monkeypatch.setattr(links, "conv_link_tx", lambda tr, modem, frames, bits, seed, first, sigma: (calls.append((frames, bits, seed, first)) or (None, None)))
+    monkeypatch.setenv("RANK", "3"); monkeypatch.setenv("WORLD_SIZE", "4")
+    link = links.ConvLinkGPU(helpers.k7(), QAMModem(4), frame_bits=64, frames_per_batch=10, seed=9)
+    link.make_batch(6.0, 5)
+    assert calls == [(10, 64, 9, (5 * 4 + 3) * 10)]
