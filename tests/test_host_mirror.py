@@ -85,6 +85,32 @@ def test_puncturing_roundtrip_shapes():
         depuncturing(p[:3], pv, 20)
 
 
+def test_puncturing_depuncturing_and_punctured_encoder_match_reference_golden():
+    """convcode.py:752-804 and :475-558 replayed from tests/golden/puncture.npz (oracle/make_puncture_golden.py ran the
+    reference): same outputs, and the same exception type where the reference raises."""
+    g = np.load(os.path.join(GOLD, "puncture.npz"))
+    raised = 0
+    for i in range(int(g["n_punct"])):
+        k = "p%02d" % i
+        msg, pv = g[k + "_msg"], g[k + "_pv"]
+        p = puncturing(msg, pv)
+        assert np.array_equal(p, g[k + "_punct"]), k
+        err = str(g[k + "_err"])
+        soft = p.astype(float) * 2 - 1
+        if err:
+            raised += 1
+            with pytest.raises(IndexError):
+                depuncturing(soft, pv, len(msg))
+            assert err == "IndexError"
+        else:
+            assert np.array_equal(depuncturing(soft, pv, len(msg)), g[k + "_depunct"]), k
+    tr = helpers.k7()
+    for i in range(int(g["n_enc"])):
+        k = "e%02d" % i
+        got = conv_encode(g[k + "_msg"], tr, str(g[k + "_term"]), g[k + "_pm"])
+        assert np.array_equal(got, g[k + "_coded"]), k
+
+
 def test_interleaver_and_turbo_encode():
     il = RandInterlv(64, 1)
     assert np.array_equal(np.sort(il.p_array), np.arange(64))
