@@ -45,8 +45,14 @@ class AwgnSisoChannel:
 
     def propagate(self, msg):
         msg = np.asarray(msg)
-        self.channel_gains = np.ones(len(msg), dtype=complex if self.isComplex else float)
         self.noises = self.generate_noises(len(msg))
+        # SISOFlatChannel draws its fading variates after the noise even when their variance is zero
+        # (channels.py:213-217); the same draws are made and discarded here so that a seeded run consumes the random
+        # stream exactly like the reference with fading_param = (1 + 0j, 0j) and reproduces its BERs to the last digit.
+        self.rng.standard_normal(len(msg))
+        if self.isComplex:
+            self.rng.standard_normal(len(msg))
+        self.channel_gains = np.ones(len(msg), dtype=complex if self.isComplex else float)
         self.unnoisy_output = msg
         return msg + self.noises
 

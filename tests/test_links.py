@@ -34,6 +34,29 @@ def test_linkmodel_host_loop_bpsk_matches_theory():
     assert seen["n"] == 1
 
 
+def test_linkmodel_reproduces_reference_bers_for_the_same_seed():
+    """`LinkModel.link_performance` + `AwgnSisoChannel` consume numpy's global random stream exactly like the reference's
+    loop (links.py:313-337) with `SISOFlatChannel(None, (1 + 0j, 0j))` (channels.py:181-221), so a seeded run gives the
+    reference's BERs to the last digit.  Expected values: the reference itself, run in the build container with
+    np.random.seed(seed), PSKModem(4), SNRs (0, 4, 8) dB, send_max 20000, err_min 200, send_chunk 600 and a nearest-point
+    hard receiver."""
+    from commpy_b200.modulation import PSKModem
+    expected = {5: (303 / 1800, 223 / 3600, 135 / 20400), 6: (274 / 1800, 207 / 3600, 146 / 20400)}
+    for seed, want in expected.items():
+        np.random.seed(seed)
+        modem = PSKModem(4)
+        cst = np.asarray(modem.constellation)
+        nb = modem.num_bits_symbol
+
+        def receive(y, H, constellation, noise_var):
+            idx = np.abs(np.asarray(y)[:, None] - cst[None, :]).argmin(1)
+            return ((idx[:, None] >> np.arange(nb - 1, -1, -1)) & 1).reshape(-1)
+
+        model = LinkModel(modem.modulate, AwgnSisoChannel(True), receive, nb, modem.constellation, modem.Es)
+        bers = link_performance(model, np.arange(0, 9, 4), 20000, 200, 600)
+        assert np.allclose(bers, want, rtol=0, atol=1e-12), (seed, bers)
+
+
 def test_ff_taps_and_chunk_rounding():
     t = _ff_taps(helpers.k7())
     assert t.shape == (2, 7)
