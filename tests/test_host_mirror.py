@@ -168,6 +168,38 @@ def test_ldpc_design_loader(tmp_path):
     assert np.array_equal(H2, H)
 
 
+def test_ldpc_design_loader_and_encoder_match_reference_golden(tmp_path):
+    """ldpc.py:51-141 and :302-354 replayed from tests/golden/ldpc_design.npz (oracle/make_ldpc_design_golden.py ran the
+    reference on its own design files): the design is re-written with write_ldpc_params from the stored matrix, loaded
+    back, and every array of the parameter dict, the generator matrix and the encoded words must equal the reference's."""
+    import scipy.sparse as sp
+    from commpy_b200.channelcoding import triang_ldpc_systematic_encode, write_ldpc_params
+    g = np.load(os.path.join(GOLD, "ldpc_design.npz"))
+    for tag in ("g96", "w1440"):
+        n, m = int(g[tag + "_n_vnodes"]), int(g[tag + "_n_cnodes"])
+        H = sp.csc_matrix((np.ones(len(g[tag + "_H_rows"]), np.int8), (g[tag + "_H_rows"], g[tag + "_H_cols"])), shape=(m, n))
+        path = os.path.join(tmp_path, tag + ".txt")
+        write_ldpc_params(H.toarray(), path)
+        p = get_ldpc_code_params(path, True)
+        for k in ("n_vnodes", "n_cnodes", "max_cnode_deg", "max_vnode_deg", "cnode_deg_list", "vnode_deg_list"):
+            assert np.array_equal(np.asarray(p[k]), g[tag + "_" + k]), (tag, k)
+        # neighbour lists: the same sets per node (the Gallager file lists neighbours unsorted, the writer sorts them);
+        # for the WiMax design, whose file is sorted, every array including the edge maps is identical
+        for adj, deg, cnt in (("cnode_adj_list", "cnode_deg_list", m), ("vnode_adj_list", "vnode_deg_list", n)):
+            a = np.asarray(p[adj]).reshape(cnt, -1)
+            b = g[tag + "_" + adj].reshape(cnt, -1)
+            for i in range(cnt):
+                d = int(p[deg][i])
+                assert sorted(a[i, :d]) == sorted(b[i, :d]), (tag, adj, i)
+        if tag == "w1440":
+            for k in ("cnode_adj_list", "cnode_vnode_map", "vnode_adj_list", "vnode_cnode_map"):
+                assert np.array_equal(np.asarray(p[k]), g[tag + "_" + k]), (tag, k)
+        assert (p["parity_check_matrix"] != H).nnz == 0
+        assert np.array_equal(p["generator_matrix"].toarray(), g[tag + "_G"])
+        assert np.array_equal(triang_ldpc_systematic_encode(g[tag + "_msg"], p, False), g[tag + "_coded"])
+        assert np.array_equal(triang_ldpc_systematic_encode(g[tag + "_msg"][:, 0].copy(), p, False), g[tag + "_coded_padless_1d"])
+
+
 def test_batch_encoder_helper_matches_conv_encode():
     rs = np.random.RandomState(9)
     for tr in helpers.reference_test_trellises() + [helpers.k7(), helpers.rsc_k4()]:
