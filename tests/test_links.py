@@ -57,6 +57,28 @@ def test_linkmodel_reproduces_reference_bers_for_the_same_seed():
         assert np.allclose(bers, want, rtol=0, atol=1e-12), (seed, bers)
 
 
+def test_full_metrics_loop_reproduces_reference_for_the_same_seed():
+    """`LinkModel.link_performance_full_metrics` (links.py:155-267) with np.random.seed(11), PSKModem(4), SNRs (0, 4, 8) dB,
+    tx_max 40, err_min 100, send_chunk 600: bit errors per transmission exactly as the reference produced them in the
+    build container."""
+    from commpy_b200.modulation import PSKModem
+    np.random.seed(11)
+    modem = PSKModem(4)
+    cst = np.asarray(modem.constellation)
+
+    def receive(y, H, constellation, noise_var):
+        idx = np.abs(np.asarray(y)[:, None] - cst[None, :]).argmin(1)
+        return ((idx[:, None] >> np.arange(1, -1, -1)) & 1).reshape(-1)
+
+    model = LinkModel(modem.modulate, AwgnSisoChannel(True), receive, 2, modem.constellation, modem.Es)
+    BERs, BEs, CEs, NCs = model.link_performance_full_metrics(np.arange(0, 9, 4), 40, 100, 600)
+    want = [[95, 88], [41, 23, 30, 33], [2, 5, 1, 5, 6, 5, 5, 4, 3, 6, 2, 4, 2, 3, 2, 3, 6, 9, 1, 3, 7, 4, 1, 3, 4, 5]]
+    for i, row in enumerate(want):
+        assert list(np.asarray(BEs)[i, :len(row)]) == row and not np.asarray(BEs)[i, len(row):].any()
+        assert np.asarray(NCs)[i].sum() == len(row)
+        assert abs(BERs[i] - sum(row) / (600 * len(row))) < 1e-12
+
+
 def test_ff_taps_and_chunk_rounding():
     t = _ff_taps(helpers.k7())
     assert t.shape == (2, 7)
