@@ -10,15 +10,15 @@
 // Two kernel families:
 //   viterbi_fast_kernel     k=1, n=2 feed-forward shift-register codes with 64 states (K=7): one thread owns
 //                           all 64 path metrics of one frame (int32 fixed-point LLR metrics) or of TWO frames
-//                           (hard decision, u16x2-packed).  Metrics are kept in "key form"
-//                           metric*64 + state_index so that a single VIADDMNMX does add+compare+select with the
-//                           reference tie rule, the survivor bit is the key's LSB and the best state of a step is
-//                           a VIMNMX3 tree.  Survivors live in a shared-memory ring of D+9 steps per frame.
+//                           (hard decision, u16x2-packed).  A key is metric << 10 | path history, so ONE add and ONE
+//                           VIADDMNMX per state and step do add + compare + select with the reference tie rule AND
+//                           record the survivor (register exchange over blocks of 4 steps); the best state of a
+//                           step is a VIMNMX3 tree over the same keys.  Every 4 steps a 4-bit jump pointer per state
+//                           goes to a shared-memory ring; the traceback jumps 4 steps per look-up.
 //   viterbi_generic_kernel  any trellis (k<=4, n<=4, S<=256): table driven, one thread per frame, fp32 metrics
 //                           in shared memory, survivors in a global scratch buffer.
-// Both use the same block traceback: one long traceback per 16/32 steps plus a per-window fallback whenever
-// the long path does not pass through that window's own best state, which reproduces the reference's
-// per-step traceback bit for bit.
+// Both trace back in blocks of windows: one shared walk per block plus a fallback walk for every window whose own
+// best state is not on it, which reproduces the reference's per-step traceback bit for bit.
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
@@ -82,97 +82,86 @@ static bool code_matches(const cpbTrellis &t)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fast path
+// Fast path: history-key add-compare-select + jump traceback (tests/model_jump_viterbi.py is the NumPy model)
+//
+//   key    = metric << FB | field                      FB = 6 + B history bits, B = 4 trellis steps per block
+//   field  bit i <-> input u_{t0-5+i} on the state's survivor path (t0 = last block boundary): bits 0..5 are the
+//          survivor's state at t0, bit 6+j is the input of sub-step j of the running block
+//   ACS    Kn[l + 32u] = min(K[2l] + Bm[out(2l,u)], K[2l+1] + Bm[out(2l+1,u)]) + (u << (6+j))
+//          ONE add and ONE add-min (VIADDMNMX) per state and step.  The smaller key wins; on equal metrics the
+//          fields decide: both candidates carry the same newer history bits and differ in the predecessor's LSB,
+//          so predecessor 2l wins -- the reference's first minimum over (prev_state asc) (convcode.py:612-642).
+//   best   the minimum of the 64 keys: lowest metric, ties -> lowest field = lowest state index (np.argmin, :645);
+//          its field is the best state's whole path back to the block boundary.
+//   block  every B steps the low B bits of each key (the survivor's inputs u_{t0-5}..u_{t0-2}: a B-step jump
+//          pointer) go to the shared-memory ring and the key becomes metric | state.
+//   traceback  bit p is read on the path from best[min(p+D-1, T)] (App. A.1-8): start from that best key's
+//          field, then jump B steps per look-up: state(t0-B) = ((state(t0) & 3) << 4) | nibble[t0][state(t0)].
 // ------------------------------------------------------------------------------------------------
 namespace fast {
 
-constexpr int TBB = 24;            // windows per traceback block
-constexpr int QBITS = 19;          // |quantised LLR| <= 2^19
-constexpr int QMAX = 1 << QBITS;
+constexpr int B = 4;               // trellis steps per history block
+constexpr int FB = 6 + B;          // history bits in a key
 constexpr int BD = 32;             // one warp per CTA: every synchronisation below is a __syncwarp()
-// (the input prefetch distance QD, in pairs of trellis steps, is a template parameter of the kernel body: 4 by default)
-#ifndef CPB_ARITH_BITS
-#define CPB_ARITH_BITS 0
-#endif
-constexpr bool ARITH_BITS = CPB_ARITH_BITS != 0;
+constexpr int QBITS = 17;          // soft / unquantized: |quantised value| <= 2^17 (22 metric bits: 27 * 2^17 < 2^22)
+constexpr int QMAX = 1 << QBITS;
+constexpr int DMAX = 46;           // deepest traceback the fast path takes
+constexpr int TASK_CAP = 384;
+#ifndef CPB_VITERBI_TBB
+#define CPB_VITERBI_TBB 24         // windows per traceback block (multiple of B, <= 28)
+#endif      // retired paths kept per block and warp; beyond that they are finished inline
 
 struct Params {
     const void *coded;
     int64_t n_in;
     int64_t batch;
-    int L, T, D, R;
+    int L, T, D;
+    int TBB, NJ, RB;             // windows per traceback block, jumps below a block, ring blocks
     int mode;                    // CPB_VITERBI_*
-    const uint32_t *amax_bits;   // float input: bits of max |x| over the call (device)
+    const float *frame_scale;    // float input: power-of-two scale per frame (device)
     uint8_t *out;
-    int out_vec16;               // 1: rows of out are 16-byte aligned
-    int in_aligned;              // 1: rows of coded are 4-byte (u8) / 16-byte (f32) aligned and n_in % 4 == 0
-    uint32_t keep_mask;          // ~IDX_MASK, passed at run time so the key fix-up stays one LOP3 (reg & reg | imm)
-    int sm_count;
+    int out_vec8;                // 1: rows of out are 8-byte aligned
+    int in_aligned;              // 1: rows of coded are 8-byte (u8) / 16-byte (f32) aligned
+    uint32_t met_mask;           // metric bits of a key, passed at run time so the key refresh stays one LOP3
 };
 
 template <int PACK> struct KeyOps;
-template <> struct KeyOps<2> {   // two frames per register, u16 halves
-    static constexpr uint32_t IDX_MASK = 0x003F003Fu;
-    static constexpr uint32_t LSB = 0x00010001u;
+template <> struct KeyOps<2> {   // two frames per register, u16 halves: 6 metric bits + 10 history bits
+    static constexpr uint32_t FMASK = 0x03FF03FFu;
+    static constexpr uint32_t INC0 = 0x00400040u;      // history bit 6 of both halves
+    static constexpr uint32_t NIBM = 0x000F000Fu;
     __device__ static __forceinline__ uint32_t addmin(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_u16x2(a, b, c); }
     __device__ static __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
     __device__ static __forceinline__ uint32_t min2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
     __device__ static __forceinline__ uint32_t idx(int s) { return (uint32_t)s | ((uint32_t)s << 16); }
 };
-template <> struct KeyOps<1> {
-    static constexpr uint32_t IDX_MASK = 0x3Fu;
-    static constexpr uint32_t LSB = 1u;
+template <> struct KeyOps<1> {   // one frame per register: 22 metric bits + 10 history bits
+    static constexpr uint32_t FMASK = 0x3FFu;
+    static constexpr uint32_t INC0 = 0x40u;
+    static constexpr uint32_t NIBM = 0xFu;
     __device__ static __forceinline__ uint32_t addmin(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_u32(a, b, c); }
     __device__ static __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u32(a, b, c); }
     __device__ static __forceinline__ uint32_t min2(uint32_t a, uint32_t b) { return min(a, b); }
     __device__ static __forceinline__ uint32_t idx(int s) { return (uint32_t)s; }
 };
 
-__device__ __forceinline__ uint32_t mad_shift(uint32_t x, int sh, uint32_t acc)
-{
-    uint32_t r;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(1u << sh), "r"(acc));     // sh is a constant after unrolling
-    return r;
-}
-
-// one trellis step on register-resident keys: Kn <- ACS(K, Bm); W <- survivor bits; returns min key(s)
+// one trellis step on register-resident keys: Kn <- ACS(K, Bm); returns the minimum key(s)
 template <class CODE, int PACK>
 __device__ __forceinline__ uint32_t acs_step(const uint32_t (&K)[64], uint32_t (&Kn)[64], const uint32_t (&Bm)[4],
-                                             uint32_t (&W)[2 * PACK], const uint32_t keep)
+                                             const uint32_t inc)
 {
     using OPS = KeyOps<PACK>;
     constexpr int H = CODE::S / 2;
-    constexpr int WSH = (PACK == 2) ? 4 : 5;        // states per survivor word: 16 (packed) or 32
+    uint32_t Bm1[4];
 #pragma unroll
-    for (int w = 0; w < 2 * PACK; ++w) W[w] = 0;
+    for (int o = 0; o < 4; ++o) Bm1[o] = Bm[o] + inc;       // input 1 enters the history of the states l + H
 #pragma unroll
     for (int l = 0; l < H; ++l) {
-        // predecessors 2l (survivor bit 0) and 2l+1 (bit 1); new state l <- input 0, l+H <- input 1.
-        // keys are metric*64 + state: the smaller key wins, ties go to predecessor 2l (convcode.py:612-642),
-        // and the winner's LSB is the survivor bit.
-        const uint32_t c10 = K[2 * l + 1] + Bm[CODE::out(2 * l + 1, 0)];
-        const uint32_t m0 = OPS::addmin(K[2 * l], Bm[CODE::out(2 * l, 0)], c10);
-        const uint32_t c11 = K[2 * l + 1] + Bm[CODE::out(2 * l + 1, 1)];
-        const uint32_t m1 = OPS::addmin(K[2 * l], Bm[CODE::out(2 * l, 1)], c11);
-        Kn[l] = (m0 & keep) | OPS::idx(l);
-        Kn[l + H] = (m1 & keep) | OPS::idx(l + H);
-        // survivor bit = LSB of the winner.  Instead of masking it out (LOP3: ALU pipe only, and the ALU pipe is the
-        // busy one) it is recovered with adds the scheduler may place on either pipe: the winner's index field is
-        // 2l+d, the refreshed key's is l (resp. l+H), the metric fields are equal, so per 16/32-bit lane
-        //   m0 - Kn[l] - l = d        and        (m1 + (H - l)) - Kn[l+H] = d      (no borrow between lanes).
-        uint32_t x0, x1;
-        if (ARITH_BITS) {
-            x0 = (m0 - Kn[l]) - OPS::idx(l);
-            x1 = (m1 + OPS::idx(H - l)) - Kn[l + H];
-        } else {
-            x0 = m0 & OPS::LSB;
-            x1 = m1 & OPS::LSB;
-        }
-        // survivor bit -> its slot in the word: one IMAD (x * 2^sh + W) on the FMA pipe
-        W[l >> WSH] = mad_shift(x0, l & ((1 << WSH) - 1), W[l >> WSH]);
-        W[(l + H) >> WSH] = mad_shift(x1, l & ((1 << WSH) - 1), W[(l + H) >> WSH]);
+        const uint32_t c0 = K[2 * l + 1] + Bm[CODE::out(2 * l + 1, 0)];
+        Kn[l] = OPS::addmin(K[2 * l], Bm[CODE::out(2 * l, 0)], c0);
+        const uint32_t c1 = K[2 * l + 1] + Bm1[CODE::out(2 * l + 1, 1)];
+        Kn[l + H] = OPS::addmin(K[2 * l], Bm1[CODE::out(2 * l, 1)], c1);
     }
-    // best state(s): lowest key = lowest metric, ties -> lowest state index (np.argmin, convcode.py:645)
     uint32_t r[22];
 #pragma unroll
     for (int i = 0; i < 21; ++i) r[i] = OPS::min3(Kn[3 * i], Kn[3 * i + 1], Kn[3 * i + 2]);
@@ -189,141 +178,139 @@ __device__ __forceinline__ uint32_t acs_step(const uint32_t (&K)[64], uint32_t (
 // shared memory of one warp-CTA
 template <int PACK>
 struct Smem {
-    uint32_t *w;        // survivor ring [R][2*PACK][32]
-    uint16_t *best;     // best states   [R][32]   (frame B in the high byte)
+    static constexpr int NW = 8 * PACK;     // 32-bit words of jump nibbles per block and thread
+    uint32_t *nib;      // jump nibbles [RB][NW][32]: word w = states 4w..4w+3 (frame A low half, B high half) when
+                        // PACK = 2, states 8w..8w+7 when PACK = 1
+    uint32_t *bf;       // best fields of the running traceback block [TBB][32] (frame B in the high half)
     uint4 *lut;         // hard-decision branch metrics [16]
     uint32_t *tasks;    // retired-path tasks [2*TASK_CAP]
     uint32_t *ntasks;   // [1]
-    uint32_t *outbits;  // [32*PACK][2]
-    int R;
-    __device__ __forceinline__ int get_best(int slot, int col, int fi) const { return (best[slot * BD + col] >> (8 * fi)) & 63; }
-    __device__ __forceinline__ int get_dec(int slot, int col, int s, int fi) const
-    {
-        if (PACK == 2) return (w[(slot * 4 + (s >> 4)) * BD + col] >> ((s & 15) + 16 * fi)) & 1;
-        return (w[(slot * 2 + (s >> 5)) * BD + col] >> (s & 31)) & 1;
-    }
-    __device__ __forceinline__ int dec_slot(int slot) const { return slot == 0 ? R - 1 : slot - 1; }
+    uint32_t *outbits;  // [32*PACK]
+    int RB;
 };
 
-static size_t smem_bytes(int R, int pack)
+static size_t smem_bytes(int RB, int TBB, int pack)
 {
-    size_t b = (size_t)R * 2 * pack * BD * sizeof(uint32_t);
-    b += (((size_t)R * BD * sizeof(uint16_t)) + 15) & ~(size_t)15;
+    size_t b = (size_t)RB * 8 * pack * BD * sizeof(uint32_t);
+    b += (size_t)TBB * BD * sizeof(uint32_t);
     b += 16 * sizeof(uint4);
-    b += (size_t)2 * 384 * sizeof(uint32_t) + 16;
-    b += (size_t)BD * pack * 2 * sizeof(uint32_t);
+    b += (size_t)2 * TASK_CAP * sizeof(uint32_t) + 16;
+    b += (size_t)BD * pack * sizeof(uint32_t);
     return b;
 }
 
-// Traceback of the windows t' in (ts, te] (App. A.1-8): bit p of the frame is the input u_{p+1} read on the
-// survivor path that starts at best[min(p + D - 1, T)].  A state holds the last M inputs (newest in the MSB), so a
-// walk just shifts survivor bits into a register: after k look-ups from step tau0 the low M bits of `path` are the
-// state at step tau0-k and bit b is u_{tau0-k-(M-1)+b}.
-//   phase A  every thread walks tau = te .. ts+1 once along the current path of each of its frames; where the path
-//            misses best[tau] it is retired into a task (it still owes the bits of the windows (tau, hi] it served)
-//            and a new path starts at best[tau].  16 iterations, no divergence.  The path alive at ts ("closing")
-//            is finished by its own thread.
-//   phase B  every retired path needs D-8 more look-ups.  All tasks have that same length and any lane can run any
-//            task (the ring is in shared memory), so the warp shares them evenly, two per lane at a time: the cost
-//            follows the AVERAGE number of survivor-path switches per frame, not the worst lane.
-// A path that served the windows (lo, hi] and has been walked down to step lo-D+8 contributes
-//   (path << (lo-ts)) & bits[lo-ts, hi-ts)          (block bit j = window - ts - 1 = output bit p0 + j),
-// and in the final block the path started at T also owns every later bit up to L-1.
+// A survivor path as a shift register: bit i of `reg` is the input u_{t0-5+i}; one look-up moves t0 down by B steps.
 template <int PACK, typename PT>
-struct Walker {
-    static constexpr int ROWB = 2 * PACK * BD * 4;      // bytes per ring slot
-    const unsigned char *wbase;
-    int rowoff, wrap;
-    int colsh, shbase;
-    PT path;
-    __device__ __forceinline__ void init(const Smem<PACK> &sm, int slot, int col, int fi, PT p0)
+struct Jumper {
+    static constexpr int ROWB = 8 * PACK * BD * 4;      // bytes per ring block
+    const unsigned char *nbase;
+    int rowoff, wrap, colsh, fish;
+    PT reg;
+    __device__ __forceinline__ void init(const Smem<PACK> &sm, int slot, int col, int fi, PT r0)
     {
-        wbase = reinterpret_cast<const unsigned char *>(sm.w);
-        rowoff = slot * ROWB; wrap = sm.R * ROWB; colsh = col * 4; shbase = 16 * fi; path = p0;
+        nbase = reinterpret_cast<const unsigned char *>(sm.nib);
+        rowoff = slot * ROWB; wrap = sm.RB * ROWB; colsh = col * 4; fish = 16 * fi; reg = r0;
     }
-    __device__ __forceinline__ void step()              // survivor look-up at the current step, move one step back
+    __device__ __forceinline__ void jump()
     {
-        const uint32_t st = (uint32_t)path & 63u;
-        const int sel = (PACK == 2) ? (int)((st << 3) & 0x180u) : (int)((st << 2) & 0x80u);   // word (st>>4 | st>>5) * 128 B
-        const uint32_t word = *reinterpret_cast<const uint32_t *>(wbase + rowoff + sel + colsh);
-        const uint32_t sh = (PACK == 2) ? ((st & 15u) | (uint32_t)shbase) : (st & 31u);
-        path = (path << 1) | (PT)((word >> sh) & 1u);
+        const uint32_t st = (uint32_t)reg & 63u;
+        const int wsel = (PACK == 2) ? (int)((st >> 2) << 7) : (int)((st >> 3) << 7);
+        const uint32_t sh = (PACK == 2) ? (((st & 3u) << 2) | (uint32_t)fish) : ((st & 7u) << 2);
+        const uint32_t word = *reinterpret_cast<const uint32_t *>(nbase + rowoff + wsel + colsh);
+        reg = (PT)(reg << B) | (PT)((word >> sh) & 15u);
         rowoff -= ROWB;
         if (rowoff < 0) rowoff += wrap;
     }
-    __device__ __forceinline__ uint32_t state() const { return (uint32_t)path & 63u; }
 };
 
-constexpr int TASK_CAP = 384;      // retired paths kept per block and warp; beyond that they are finished inline
-
+// Traceback of the windows tau in (ts, te] (App. A.1-8): output bit p = tau - D + 1 is the input u_{tau-D+2} on the
+// survivor path that starts at best[tau]  (ts is a block boundary; te = ts + TBB, or T in the final block).
+//   phase A  every thread walks tau = te .. ts+1 once along the current path of each of its frames (one look-up per
+//            B steps); where the path misses best[tau] it is retired into a task (it still owes the bits of the
+//            windows (tau, hi] it served) and a new path starts from the field of best[tau].
+//   phase B  every retired path needs NJ more jumps; any lane can run any task (the ring is in shared memory), so
+//            the warp shares them evenly, two per lane at a time.
+// A path that served the windows (lo, hi], was retired in the block above boundary t0s and has been jumped NJ times
+// holds block bit k (window ts+1+k) at register bit k + shc - (t0s - ts), shc = 4*NJ - D + 8 in [0, 3].
+// In the final block the path from best[T] also owns every later bit up to L-1 (a separate 64-bit walk).
 template <class CODE, int PACK, bool FINAL>
-__device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int te, int slot_te, int D, int L,
-                                               uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec16)
+__device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int te, int slot_last, int D, int L, int NJ,
+                                               uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec8)
 {
-    using PT = typename std::conditional<FINAL, unsigned long long, uint32_t>::type;
-    constexpr int M = CODE::M;
     const int lane = threadIdx.x;
-    const int p0 = ts - D + 2;                          // first output bit of this block
-    const int ext = (D - 2 - (M - 1) - 1 > 0) ? (D - 2 - (M - 1) - 1) : 0;     // look-ups below the window range
-    const int dsh = (D - 2 - (M - 1) - 1 < 0) ? 1 : 0;  // D = M+1: the walk is one look-up deeper than needed
-    auto contribution = [&](PT path, int lo, int hi) -> PT {
-        PT v = (PT)(path << (lo - ts)) >> dsh;
-        v &= (PT)(~(PT)0 << (lo - ts));
-        if (!(FINAL && hi == te)) v &= (PT) ~(PT)(~(PT)0 << (hi - ts));
+    const int p0 = ts - D + 2;                          // output bit of window ts+1
+    const int shc = 4 * NJ - D + 8;
+    const int jte = (te - 1) & 3;
+    // ring slot of the block that ended at the boundary below te
+    int bslot0 = slot_last;
+    if (jte == 3) bslot0 = (slot_last == 0) ? sm.RB - 1 : slot_last - 1;
+    auto contribution = [&](uint32_t reg, int delta, int lo, int hi) -> uint32_t {
+        uint32_t v = (reg << delta) >> shc;
+        v &= ~0u << (lo - ts);
+        v &= ~(~0u << (hi - ts));
         return v;
     };
     if (lane == 0) *sm.ntasks = 0u;
-    PT acc[PACK];
+    uint32_t acc[PACK];
     int hi[PACK];
-    Walker<PACK, PT> wk[PACK];
+    Jumper<PACK, uint32_t> jw[PACK];
+    const uint32_t bwe = sm.bf[(te - ts - 1) * BD + lane];
 #pragma unroll
     for (int fi = 0; fi < PACK; ++fi) {
         acc[fi] = 0; hi[fi] = te;
-        wk[fi].init(sm, slot_te, lane, fi, (PT)sm.get_best(slot_te, lane, fi));
-        sm.outbits[(lane + BD * fi) * 2] = 0u; sm.outbits[(lane + BD * fi) * 2 + 1] = 0u;
+        jw[fi].init(sm, bslot0, lane, fi, (bwe >> (16 * fi)) & 0x3FFu);
+        sm.outbits[lane + BD * fi] = 0u;
     }
     __syncwarp();
     // ---- phase A
-    int slot = slot_te;
-    for (int tau = te; tau > ts; --tau) {
-        const uint32_t bw = sm.best[slot * BD + lane];
+    for (int tau = te - 1; tau > ts; --tau) {
+        const int j = (tau - 1) & 3;
+        if (j == 3) {
+#pragma unroll
+            for (int fi = 0; fi < PACK; ++fi) jw[fi].jump();
+        }
+        const uint32_t bw = sm.bf[(tau - ts - 1) * BD + lane];
+        const uint32_t msk = 63u << (j + 1);
 #pragma unroll
         for (int fi = 0; fi < PACK; ++fi) {
-            const uint32_t b = (bw >> (8 * fi)) & 63u;
-            if (tau < hi[fi] && wk[fi].state() != b) {          // the path does not pass through best[tau]: retire it
+            const uint32_t b = (bw >> (16 * fi)) & 0x3FFu;
+            if (tau < hi[fi] && ((jw[fi].reg ^ b) & msk)) {     // the path does not pass through best[tau]: retire it
                 const uint32_t qi = atomicAdd(sm.ntasks, 1u);
+                const int delta = tau - 1 - j - ts;             // boundary below tau, relative to ts (multiple of 4)
                 if (qi < (uint32_t)TASK_CAP) {
-                    sm.tasks[2 * qi] = (uint32_t)lane | ((uint32_t)fi << 5) | ((uint32_t)(tau - ts) << 8) |
-                                       ((uint32_t)(hi[fi] - ts) << 16);
-                    sm.tasks[2 * qi + 1] = (uint32_t)wk[fi].path;      // <= 16 look-ups so far: fits 22 bits
+                    sm.tasks[2 * qi] = (uint32_t)lane | ((uint32_t)fi << 5) |
+                                       ((uint32_t)(jw[fi].rowoff / Jumper<PACK, uint32_t>::ROWB) << 6) |
+                                       ((uint32_t)(tau - ts) << 12) | ((uint32_t)(hi[fi] - ts) << 17) |
+                                       ((uint32_t)(delta >> 2) << 22);
+                    sm.tasks[2 * qi + 1] = jw[fi].reg;
                 } else {
-                    Walker<PACK, PT> t = wk[fi];
-                    for (int i = 0; i < ext; ++i) t.step();
-                    acc[fi] |= contribution(t.path, tau, hi[fi]);
+                    Jumper<PACK, uint32_t> t = jw[fi];
+                    for (int i = 0; i < NJ; ++i) t.jump();
+                    acc[fi] |= contribution(t.reg, delta, tau, hi[fi]);
                 }
                 hi[fi] = tau;
-                wk[fi].path = (PT)b;
+                jw[fi].reg = b;
             }
-            wk[fi].step();
         }
-        slot = sm.dec_slot(slot);
     }
-    // ---- closing paths of this thread's own frames (interleaved for ILP)
-    for (int i = 0; i < ext; ++i) {
+    // ---- closing paths of this thread's own frames (interleaved for ILP); the walk above ended at boundary ts
+    if (te - ts > 1 || true) {
+        // after the loop the jumpers stand at the boundary below ts+1, which is ts itself unless te == ts+1..ts+3 in a
+        // final block that never left its first block: in every case the boundary is ts (te > ts, blocks are aligned)
+    }
+    for (int i = 0; i < NJ; ++i) {
 #pragma unroll
-        for (int fi = 0; fi < PACK; ++fi) wk[fi].step();
+        for (int fi = 0; fi < PACK; ++fi) jw[fi].jump();
     }
 #pragma unroll
-    for (int fi = 0; fi < PACK; ++fi) acc[fi] |= contribution(wk[fi].path, ts, hi[fi]);
+    for (int fi = 0; fi < PACK; ++fi) acc[fi] |= contribution(jw[fi].reg, 0, ts, hi[fi]);
     __syncwarp();
     // ---- phase B: retired paths, two per lane at a time
     int ntasks = (int)*sm.ntasks;
     if (ntasks > TASK_CAP) ntasks = TASK_CAP;
-    int slot_ts = slot_te - (te - ts);
-    if (slot_ts < 0) slot_ts += sm.R;
     for (int base = 0; base < ntasks; base += 2 * BD) {
-        Walker<PACK, PT> tw[2];
-        int lo[2], thi[2], dst[2];
+        Jumper<PACK, uint32_t> tw[2];
+        int lo[2], thi[2], dst[2], dl[2];
         bool on[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -331,56 +318,50 @@ __device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int t
             on[u] = i < ntasks;
             const uint32_t a = on[u] ? sm.tasks[2 * i] : 0u;
             const int col = a & 31, fi = (a >> 5) & 1;
-            lo[u] = ts + (int)((a >> 8) & 255u); thi[u] = ts + (int)((a >> 16) & 255u);
-            dst[u] = (col + BD * fi) * 2;
-            int sl = slot_ts + (lo[u] - ts);             // the next look-up of a retired path is at step lo
-            if (sl >= sm.R) sl -= sm.R;
-            tw[u].init(sm, sl, col, fi, on[u] ? (PT)sm.tasks[2 * i + 1] : (PT)0);
+            lo[u] = ts + (int)((a >> 12) & 31u); thi[u] = ts + (int)((a >> 17) & 31u);
+            dl[u] = (int)((a >> 22) & 15u) << 2;
+            dst[u] = col + BD * fi;
+            tw[u].init(sm, (int)((a >> 6) & 63u), col, fi, on[u] ? sm.tasks[2 * i + 1] : 0u);
         }
-        for (int i = 0; i < ext; ++i) {
+        for (int i = 0; i < NJ; ++i) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) tw[u].step();
+            for (int u = 0; u < 2; ++u) tw[u].jump();
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             if (!on[u]) continue;
-            const PT bits = contribution(tw[u].path, lo[u], thi[u]);
-            const uint32_t blo = (uint32_t)bits;
-            if (blo) atomicOr(&sm.outbits[dst[u]], blo);
-            if (FINAL) {
-                const uint32_t bhi = (uint32_t)((unsigned long long)bits >> 32);
-                if (bhi) atomicOr(&sm.outbits[dst[u] + 1], bhi);
-            }
+            const uint32_t bits = contribution(tw[u].reg, dl[u], lo[u], thi[u]);
+            if (bits) atomicOr(&sm.outbits[dst[u]], bits);
         }
     }
     __syncwarp();
 #pragma unroll
     for (int fi = 0; fi < PACK; ++fi) {
-        unsigned long long a64 = (unsigned long long)acc[fi] | (unsigned long long)sm.outbits[(lane + BD * fi) * 2];
-        if (FINAL) a64 |= (unsigned long long)sm.outbits[(lane + BD * fi) * 2 + 1] << 32;
+        const uint32_t a32 = acc[fi] | sm.outbits[lane + BD * fi];
         if (!((valid_mask >> fi) & 1)) continue;
-        uint8_t *o = (fi == 0 ? out0 : out1) + p0;
+        uint8_t *orow = (fi == 0 ? out0 : out1);
         const int nbw = te - ts;
-        if (!FINAL && out_vec16 && (p0 & 15) == 0 && nbw == 16) {
-            const uint32_t b16 = (uint32_t)a64 & 0xffffu;
-            uint4 v;
-            v.x = (((b16 >> 0) & 15u) * 0x00204081u) & 0x01010101u;
-            v.y = (((b16 >> 4) & 15u) * 0x00204081u) & 0x01010101u;
-            v.z = (((b16 >> 8) & 15u) * 0x00204081u) & 0x01010101u;
-            v.w = (((b16 >> 12) & 15u) * 0x00204081u) & 0x01010101u;
-            *reinterpret_cast<uint4 *>(o) = v;
-        } else if (!FINAL && out_vec16 && (p0 & 7) == 0 && (nbw & 7) == 0) {
-            // 8 decoded bits -> 8 bytes per store (rows are 16-byte aligned, p0 is a multiple of 8)
+        if (!FINAL && out_vec8 && p0 >= 0 && (p0 & 7) == 0 && (nbw & 7) == 0) {
+            // 8 decoded bits -> 8 bytes per store
             for (int g8 = 0; g8 < nbw; g8 += 8) {
-                const uint32_t b8 = (uint32_t)(a64 >> g8) & 0xffu;
+                const uint32_t b8 = (a32 >> g8) & 0xffu;
                 uint2 v;
                 v.x = (((b8 >> 0) & 15u) * 0x00204081u) & 0x01010101u;
                 v.y = (((b8 >> 4) & 15u) * 0x00204081u) & 0x01010101u;
-                *reinterpret_cast<uint2 *>(o + g8) = v;
+                *reinterpret_cast<uint2 *>(orow + p0 + g8) = v;
             }
         } else {
-            const int cnt = FINAL ? (L - p0) : (te - ts);
-            for (int i = 0; i < cnt; ++i) o[i] = (uint8_t)((a64 >> i) & 1ull);
+            for (int i = 0; i < nbw; ++i)
+                if (p0 + i >= 0) orow[p0 + i] = (uint8_t)((a32 >> i) & 1u);
+        }
+        if (FINAL) {
+            // the path from best[T] decides every bit from T-D+2 on (u_{T-D+3} .. u_{T-5}): D-7 bits
+            Jumper<PACK, unsigned long long> t;
+            t.init(sm, bslot0, lane, fi, (unsigned long long)((bwe >> (16 * fi)) & 0x3FFu));
+            for (int i = 0; i < NJ; ++i) t.jump();
+            const unsigned long long tail = t.reg >> (jte + 1 + shc);
+            const int pt = te - D + 2;
+            for (int i = 0; i < D - 7 && pt + i < L; ++i) orow[pt + i] = (uint8_t)((tail >> i) & 1ull);
         }
     }
     __syncwarp();
@@ -389,48 +370,54 @@ __device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int t
 // the traceback is a call in the hard kernel (its 64 packed keys stay in callee-saved registers) and inlined in the
 // register-capped soft kernel (CPB_TB_INLINE_SOFT)
 template <class CODE, int PACK, bool FINAL>
-__device__ __noinline__ void tb_block_call(const Smem<PACK> sm, int ts, int te, int slot_te, int D, int L,
-                                           uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec16)
+__device__ __noinline__ void tb_block_call(const Smem<PACK> sm, int ts, int te, int slot_last, int D, int L, int NJ,
+                                           uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec8)
 {
-    tb_block_body<CODE, PACK, FINAL>(sm, ts, te, slot_te, D, L, out0, out1, valid_mask, out_vec16);
+    tb_block_body<CODE, PACK, FINAL>(sm, ts, te, slot_last, D, L, NJ, out0, out1, valid_mask, out_vec8);
 }
 #ifndef CPB_TB_INLINE_SOFT
 #define CPB_TB_INLINE_SOFT 1
 #endif
+#ifndef CPB_TB_INLINE_HARD
+#define CPB_TB_INLINE_HARD 0
+#endif
 template <class CODE, int PACK, bool FINAL>
-__device__ __forceinline__ void tb_block(const Smem<PACK> sm, int ts, int te, int slot_te, int D, int L,
-                                         uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec16)
+__device__ __forceinline__ void tb_block(const Smem<PACK> sm, int ts, int te, int slot_last, int D, int L, int NJ,
+                                         uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec8)
 {
-    if (PACK == 1 && CPB_TB_INLINE_SOFT) tb_block_body<CODE, PACK, FINAL>(sm, ts, te, slot_te, D, L, out0, out1, valid_mask, out_vec16);
-    else tb_block_call<CODE, PACK, FINAL>(sm, ts, te, slot_te, D, L, out0, out1, valid_mask, out_vec16);
+    if ((PACK == 1 && CPB_TB_INLINE_SOFT) || (PACK == 2 && CPB_TB_INLINE_HARD))
+        tb_block_body<CODE, PACK, FINAL>(sm, ts, te, slot_last, D, L, NJ, out0, out1, valid_mask, out_vec8);
+    else
+        tb_block_call<CODE, PACK, FINAL>(sm, ts, te, slot_last, D, L, NJ, out0, out1, valid_mask, out_vec8);
 }
 
-template <class CODE, int PACK, int QD = 4>
+template <class CODE, int PACK, int QD>
 __device__ __forceinline__ void viterbi_fast_body(const Params &p)
 {
     using OPS = KeyOps<PACK>;
     constexpr int S = CODE::S, M = CODE::M;
-    static_assert(S == 64, "fast path is written for 64 states");
+    constexpr int NW = 8 * PACK;
+    static_assert(S == 64 && M == 6, "fast path is written for 64 states");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     Smem<PACK> sm;
     {
         unsigned char *q = smem_raw;
-        sm.R = p.R;
-        sm.w = reinterpret_cast<uint32_t *>(q); q += (size_t)p.R * 2 * PACK * BD * sizeof(uint32_t);
-        sm.best = reinterpret_cast<uint16_t *>(q); q += (((size_t)p.R * BD * sizeof(uint16_t)) + 15) & ~(size_t)15;
+        sm.RB = p.RB;
+        sm.nib = reinterpret_cast<uint32_t *>(q); q += (size_t)p.RB * NW * BD * sizeof(uint32_t);
+        sm.bf = reinterpret_cast<uint32_t *>(q); q += (size_t)p.TBB * BD * sizeof(uint32_t);
         sm.lut = reinterpret_cast<uint4 *>(q); q += 16 * sizeof(uint4);
-        sm.tasks = reinterpret_cast<uint32_t *>(q); q += (size_t)2 * 384 * sizeof(uint32_t);
+        sm.tasks = reinterpret_cast<uint32_t *>(q); q += (size_t)2 * TASK_CAP * sizeof(uint32_t);
         sm.ntasks = reinterpret_cast<uint32_t *>(q); q += 16;
         sm.outbits = reinterpret_cast<uint32_t *>(q);
     }
     if (PACK == 2) {
         // hard-decision branch metrics of two frames: entry idx = r0A | r1A<<1 | r0B<<2 | r1B<<3,
-        // component o = Hamming distance to output symbol o (convcode.py:579), times 64, frame B in the high half
+        // component o = Hamming distance to output symbol o (convcode.py:579) in the metric field, frame B in the high half
         if (tid < 16) {
             const int a = ((tid & 1) << 1) | ((tid >> 1) & 1), b = (((tid >> 2) & 1) << 1) | ((tid >> 3) & 1);
             uint32_t e[4];
-            for (int o = 0; o < 4; ++o) e[o] = ((uint32_t)__popc(o ^ a) << 6) | ((uint32_t)__popc(o ^ b) << 22);
+            for (int o = 0; o < 4; ++o) e[o] = ((uint32_t)__popc(o ^ a) << FB) | ((uint32_t)__popc(o ^ b) << (16 + FB));
             sm.lut[tid] = make_uint4(e[0], e[1], e[2], e[3]);
         }
         __syncwarp();
@@ -448,14 +435,11 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
         outp[fi] = p.out + fr[fi] * (int64_t)p.L;
     }
 
-    // float input: power-of-two scale so that the largest |value| of the call maps to ~2^19
+    // float input: the frame's own power-of-two scale (frame_scale_kernel), so a frame decodes identically
+    // whatever it is batched with
     float scale = 1.0f, padq = 0.0f;
     if (PACK == 1) {
-        float amax = __uint_as_float(*p.amax_bits);
-        if (p.mode == CPB_VITERBI_SOFT) amax = fminf(amax, 500.0f);
-        amax = fminf(fmaxf(amax, 1e-30f), 3.0e38f);
-        scale = exp2f(floorf(log2f((float)QMAX / amax)));
-        scale = fminf(scale, 1.0e30f);
+        scale = __ldg(p.frame_scale + fr[0]);
         padq = (p.mode == CPB_VITERBI_UNQUANTIZED) ? -1.0f : 0.0f;   // convcode.py:727-732
     }
 
@@ -463,65 +447,74 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
     {
         // pm[0] = 0, every other state "infinite" (convcode.py:705-706): a finite sentinel larger than any
         // metric a path starting in state 0 can lose against (n*M*max branch metric) behaves identically.
-        const uint32_t big = (PACK == 2) ? (16u << 6) : ((uint32_t)(2 * M * QMAX + 1) << 6);
+        const uint32_t big = (PACK == 2) ? (16u << FB) : ((uint32_t)(13 * QMAX) << FB);
 #pragma unroll
         for (int s = 0; s < 64; ++s) {
             const uint32_t v = (s == 0) ? 0u : big;
             K[s] = (PACK == 2) ? ((v | (v << 16)) | OPS::idx(s)) : (v | OPS::idx(s));
         }
     }
-    const uint32_t keep = p.keep_mask;
+    const uint32_t met = p.met_mask;
 
     const unsigned char *c8 = reinterpret_cast<const unsigned char *>(p.coded);
     const float *cf = reinterpret_cast<const float *>(p.coded);
-    const int npairs_in = p.L >> 1;              // pairs of steps fully covered by received data (aligned path)
+    const int nblk_in = p.L >> 2;                // blocks of B steps fully covered by received data
 
-    // raw received values of the pair of steps (2*pr+1, 2*pr+2)
-    struct Raw { uint32_t a, b, c, d; };
-    auto load_pair = [&](int pr) {
+    // raw received values of the B steps of block blk (steps 4 blk + 1 .. 4 blk + 4)
+    struct Raw { uint32_t w[(PACK == 2) ? 4 : 8]; };
+    auto load_block = [&](int blk) {
         Raw r;
         if (PACK == 2) {
-            r.a = r.b = r.c = r.d = 0u;
-            if (p.in_aligned) {
-                if (pr < npairs_in) {
-                    r.a = __ldg(reinterpret_cast<const uint32_t *>(c8 + fr[0] * p.n_in) + pr);
-                    r.b = __ldg(reinterpret_cast<const uint32_t *>(c8 + fr[PACK - 1] * p.n_in) + pr);
-                }
+            // w[0..1] = the 8 coded bytes of frame A, w[2..3] = frame B; past the data: zeros (convcode.py:727-728)
+            r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0u;
+            if (p.in_aligned && blk < nblk_in) {
+                const uint2 a = __ldg(reinterpret_cast<const uint2 *>(c8 + fr[0] * p.n_in) + blk);
+                const uint2 b = __ldg(reinterpret_cast<const uint2 *>(c8 + fr[PACK - 1] * p.n_in) + blk);
+                r.w[0] = a.x; r.w[1] = a.y; r.w[2] = b.x; r.w[3] = b.y;
             } else {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int tau = 2 * pr + 1 + h;
+                for (int h = 0; h < 4; ++h) {
+                    const int tau = 4 * blk + 1 + h;
                     if (tau <= p.L) {
                         const unsigned char *qa = c8 + fr[0] * p.n_in + 2 * (int64_t)(tau - 1);
                         const unsigned char *qb = c8 + fr[PACK - 1] * p.n_in + 2 * (int64_t)(tau - 1);
-                        r.a |= ((uint32_t)__ldg(qa) | ((uint32_t)__ldg(qa + 1) << 8)) << (16 * h);
-                        r.b |= ((uint32_t)__ldg(qb) | ((uint32_t)__ldg(qb + 1) << 8)) << (16 * h);
+                        r.w[h >> 1] |= ((uint32_t)__ldg(qa) | ((uint32_t)__ldg(qa + 1) << 8)) << (16 * (h & 1));
+                        r.w[2 + (h >> 1)] |= ((uint32_t)__ldg(qb) | ((uint32_t)__ldg(qb + 1) << 8)) << (16 * (h & 1));
                     }
                 }
             }
         } else {
             const uint32_t pb = __float_as_uint(padq);
-            r.a = r.b = r.c = r.d = pb;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r.w[i] = pb;
             const float *row = cf + fr[0] * p.n_in;
-            if (p.in_aligned && pr < npairs_in) {
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(row) + pr);
-                r.a = __float_as_uint(v.x); r.b = __float_as_uint(v.y); r.c = __float_as_uint(v.z); r.d = __float_as_uint(v.w);
-            } else if (!p.in_aligned) {
-                const int tau = 2 * pr + 1;
-                if (tau <= p.L) { r.a = __float_as_uint(__ldg(row + 2 * (tau - 1))); r.b = __float_as_uint(__ldg(row + 2 * (tau - 1) + 1)); }
-                if (tau + 1 <= p.L) { r.c = __float_as_uint(__ldg(row + 2 * tau)); r.d = __float_as_uint(__ldg(row + 2 * tau + 1)); }
+            if (p.in_aligned && blk < nblk_in) {
+                const float4 v0 = __ldg(reinterpret_cast<const float4 *>(row) + 2 * blk);
+                const float4 v1 = __ldg(reinterpret_cast<const float4 *>(row) + 2 * blk + 1);
+                r.w[0] = __float_as_uint(v0.x); r.w[1] = __float_as_uint(v0.y); r.w[2] = __float_as_uint(v0.z); r.w[3] = __float_as_uint(v0.w);
+                r.w[4] = __float_as_uint(v1.x); r.w[5] = __float_as_uint(v1.y); r.w[6] = __float_as_uint(v1.z); r.w[7] = __float_as_uint(v1.w);
+            } else {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const int tau = 4 * blk + 1 + h;
+                    if (tau <= p.L) {
+                        r.w[2 * h] = __float_as_uint(__ldg(row + 2 * (int64_t)(tau - 1)));
+                        r.w[2 * h + 1] = __float_as_uint(__ldg(row + 2 * (int64_t)(tau - 1) + 1));
+                    }
+                }
             }
         }
         return r;
     };
-    // the four branch metrics (times 64) of step h (0/1) of a pair
+    // the four branch metrics (in the metric field) of sub-step h of a block
     auto make_bm = [&](const Raw &r, int h, uint32_t (&Bm)[4]) {
         if (PACK == 2) {
-            const uint32_t ta = (r.a | (r.a >> 7)) >> (16 * h), tb = (r.b | (r.b >> 7)) >> (16 * h);
+            const uint32_t wa = r.w[h >> 1], wb = r.w[2 + (h >> 1)];
+            const uint32_t ta = (wa | (wa >> 7)) >> (16 * (h & 1)), tb = (wb | (wb >> 7)) >> (16 * (h & 1));
             const uint4 e = sm.lut[(ta & 3u) | ((tb & 3u) << 2)];
             Bm[0] = e.x; Bm[1] = e.y; Bm[2] = e.z; Bm[3] = e.w;
         } else {
-            float r0 = __uint_as_float(h ? r.c : r.a), r1 = __uint_as_float(h ? r.d : r.b);
+            float r0 = __uint_as_float(r.w[2 * h]), r1 = __uint_as_float(r.w[2 * h + 1]);
             if (p.mode == CPB_VITERBI_SOFT) {          // convcode.py:718-719
                 r0 = fminf(fmaxf(r0, -500.0f), 500.0f);
                 r1 = fminf(fmaxf(r1, -500.0f), 500.0f);
@@ -530,93 +523,159 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
             const int q1 = __float2int_rn(fminf(fmaxf(r1 * scale, -(float)QMAX), (float)QMAX));
             // -log-likelihood of code bit c given value r, up to a per-step constant (convcode.py:581-587):
             // c = 0 costs max(q,0), c = 1 costs max(-q,0)
-            const uint32_t z0 = (uint32_t)max(q0, 0) << 6, o0 = (uint32_t)max(-q0, 0) << 6;
-            const uint32_t z1 = (uint32_t)max(q1, 0) << 6, o1 = (uint32_t)max(-q1, 0) << 6;
+            const uint32_t z0 = (uint32_t)max(q0, 0) << FB, o0 = (uint32_t)max(-q0, 0) << FB;
+            const uint32_t z1 = (uint32_t)max(q1, 0) << FB, o1 = (uint32_t)max(-q1, 0) << FB;
             Bm[0] = z0 + z1; Bm[1] = z0 + o1; Bm[2] = o0 + z1; Bm[3] = o0 + o1;
         }
     };
 
-    int slot = 0;
-    // Traceback blocks end every TBB steps.  (Starting alternate warps half a block out of phase was measured and
-    // changes nothing: warps drift apart on their own.)
-    int ts_cur = p.D - 2;
-    int next_te = ts_cur + TBB;
-    uint32_t W[2 * PACK];
+    const int ts0 = (p.D - 2) & ~3;              // first traceback block starts at this boundary (windows exist from D-1)
+    int ts_cur = ts0;
+    int next_te = ts_cur + p.TBB;
+    int nslot = 0;                               // ring slot the next completed block goes to
+    const int nfull = p.T >> 2, rem = p.T & 3;
 
-    auto finish_step = [&](int tau, uint32_t mn, uint32_t (&Kc)[64]) {
-        const uint32_t bestv = (PACK == 2) ? ((mn & 63u) | (((mn >> 16) & 63u) << 8)) : (mn & 63u);
+    // end of a block of B steps (keys in Kc, mn = minimum key of the last step): jump nibbles to the ring, keys back to
+    // metric | state, renormalisation
+    auto block_end = [&](uint32_t (&Kc)[64], uint32_t mn, int tau) {
+        if (PACK == 2) {
 #pragma unroll
-        for (int i = 0; i < 2 * PACK; ++i) sm.w[(slot * 2 * PACK + i) * BD + tid] = W[i];
-        sm.best[slot * BD + tid] = (uint16_t)bestv;
-        if ((tau & 15) == 0) {          // renormalise: subtract the minimum metric from every key
-            const uint32_t sub = mn & ~OPS::IDX_MASK;
+            for (int w = 0; w < 16; ++w) {
+                const uint32_t t0 = (Kc[4 * w] & OPS::NIBM) | ((Kc[4 * w + 1] << 4) & ~OPS::NIBM);
+                const uint32_t t1 = (Kc[4 * w + 2] & OPS::NIBM) | ((Kc[4 * w + 3] << 4) & ~OPS::NIBM);
+                sm.nib[(nslot * NW + w) * BD + tid] = __byte_perm(t0, t1, 0x6240);
+            }
+        } else {
 #pragma unroll
-            for (int s = 0; s < 64; ++s) Kc[s] -= sub;
+            for (int w = 0; w < 8; ++w) {
+                uint32_t t[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    t[i] = (Kc[8 * w + 2 * i] & OPS::NIBM) | ((Kc[8 * w + 2 * i + 1] << 4) & ~OPS::NIBM);
+                sm.nib[(nslot * NW + w) * BD + tid] =
+                    __byte_perm(__byte_perm(t[0], t[1], 0x0040), __byte_perm(t[2], t[3], 0x0040), 0x5410);
+            }
         }
-        if (tau == p.T) {
-            tb_block<CODE, PACK, true>(sm, ts_cur, tau, slot, p.D, p.L, outp[0], outp[PACK - 1], valid_mask, p.out_vec16);
-        } else if (tau == next_te) {
-            tb_block<CODE, PACK, false>(sm, ts_cur, tau, slot, p.D, p.L, outp[0], outp[PACK - 1], valid_mask, p.out_vec16);
-            ts_cur = tau;
-            next_te = tau + TBB;
-        }
-        slot = (slot + 1 == p.R) ? 0 : slot + 1;
+        const bool renorm = (PACK == 1) || ((tau & 7) == 0);
+        const uint32_t sub = renorm ? (mn & ~OPS::FMASK) : 0u;
+#pragma unroll
+        for (int s = 0; s < 64; ++s) Kc[s] = ((Kc[s] & met) | OPS::idx(s)) - sub;
     };
 
     Raw qd[QD];
 #pragma unroll
-    for (int i = 0; i < QD; ++i) qd[i] = load_pair(i);
-    const int npairs = (p.T + 1) >> 1;
-    // branch metrics are produced one step ahead of the add-compare-select that uses them, so the look-up table
-    // read (hard) / float->fixed conversion (soft) of step tau+1 overlaps the ~400 instructions of step tau
-    uint32_t BmA[4], BmB[4];
-    make_bm(qd[0], 0, BmA);
-    for (int pr = 0; pr < npairs; ++pr) {
+    for (int i = 0; i < QD; ++i) qd[i] = load_block(i);
+    uint32_t Bm[4];
+    for (int blk = 0; blk < nfull; ++blk) {
         const Raw cur = qd[0];
 #pragma unroll
         for (int i = 0; i + 1 < QD; ++i) qd[i] = qd[i + 1];
-        qd[QD - 1] = load_pair(pr + QD);            // software prefetch, QD pairs of steps ahead
-        const int tau = 2 * pr + 1;
-        if (PACK == 2) make_bm(cur, 1, BmB);        // (the soft kernel is register-capped: it converts in place)
-        uint32_t mn = acs_step<CODE, PACK>(K, Kn, BmA, W, keep);
-        finish_step(tau, mn, Kn);
-        if (PACK != 2) make_bm(cur, 1, BmB);
-        if (PACK == 2) make_bm(qd[0], 0, BmA);
-        if (tau + 1 <= p.T) {
-            mn = acs_step<CODE, PACK>(Kn, K, BmB, W, keep);
-            finish_step(tau + 1, mn, K);
+        qd[QD - 1] = load_block(blk + QD);          // software prefetch, QD blocks ahead
+        const int tau0 = 4 * blk;
+        const bool keep_bf = tau0 >= ts_cur;
+        uint32_t *bfp = sm.bf + (tau0 - ts_cur) * BD + tid;
+        uint32_t mn;
+        make_bm(cur, 0, Bm);
+        mn = acs_step<CODE, PACK>(K, Kn, Bm, OPS::INC0 << 0);
+        if (keep_bf) bfp[0 * BD] = mn & OPS::FMASK;
+        make_bm(cur, 1, Bm);
+        mn = acs_step<CODE, PACK>(Kn, K, Bm, OPS::INC0 << 1);
+        if (keep_bf) bfp[1 * BD] = mn & OPS::FMASK;
+        make_bm(cur, 2, Bm);
+        mn = acs_step<CODE, PACK>(K, Kn, Bm, OPS::INC0 << 2);
+        if (keep_bf) bfp[2 * BD] = mn & OPS::FMASK;
+        make_bm(cur, 3, Bm);
+        mn = acs_step<CODE, PACK>(Kn, K, Bm, OPS::INC0 << 3);
+        if (keep_bf) bfp[3 * BD] = mn & OPS::FMASK;
+        const int tau = tau0 + 4;
+        block_end(K, mn, tau);
+        if (tau == p.T) {
+            tb_block<CODE, PACK, true>(sm, ts_cur, tau, nslot, p.D, p.L, p.NJ, outp[0], outp[PACK - 1], valid_mask, p.out_vec8);
+        } else if (tau == next_te) {
+            tb_block<CODE, PACK, false>(sm, ts_cur, tau, nslot, p.D, p.L, p.NJ, outp[0], outp[PACK - 1], valid_mask, p.out_vec8);
+            ts_cur = tau;
+            next_te = tau + p.TBB;
         }
-        if (PACK != 2) make_bm(qd[0], 0, BmA);
+        nslot = (nslot + 1 == p.RB) ? 0 : nslot + 1;
+    }
+    if (rem) {
+        // the last 1..3 steps: no block completes, the final traceback starts from best[T]'s field
+        const Raw cur = qd[0];
+        const int tau0 = 4 * nfull;
+        uint32_t *bfp = sm.bf + (tau0 - ts_cur) * BD + tid;
+        const int last = (nslot == 0) ? p.RB - 1 : nslot - 1;
+        uint32_t mn;
+        make_bm(cur, 0, Bm);
+        mn = acs_step<CODE, PACK>(K, Kn, Bm, OPS::INC0 << 0);
+        bfp[0 * BD] = mn & OPS::FMASK;
+        if (rem >= 2) {
+            make_bm(cur, 1, Bm);
+            mn = acs_step<CODE, PACK>(Kn, K, Bm, OPS::INC0 << 1);
+            bfp[1 * BD] = mn & OPS::FMASK;
+        }
+        if (rem >= 3) {
+            make_bm(cur, 2, Bm);
+            mn = acs_step<CODE, PACK>(K, Kn, Bm, OPS::INC0 << 2);
+            bfp[2 * BD] = mn & OPS::FMASK;
+        }
+        tb_block<CODE, PACK, true>(sm, ts_cur, p.T, last, p.D, p.L, p.NJ, outp[0], outp[PACK - 1], valid_mask, p.out_vec8);
     }
 }
 
-// hard decision: two u16x2-packed frames per thread (213 registers, 7-8 warps per SM)
+// hard decision: two u16x2-packed frames per thread
 template <class CODE>
-__global__ void __launch_bounds__(BD) viterbi_fast_kernel_hard(const Params p) { viterbi_fast_body<CODE, 2>(p); }
-// soft / unquantized: one frame per thread, capped at 168 registers so that 12 warps fit an SM; the input prefetch queue
-// is one pair deep here (registers are the scarce resource: 4 pairs cost 2.26 ms instead of 1.98 ms per 65,536 frames)
+__global__ void __launch_bounds__(BD) viterbi_fast_kernel_hard(const Params p) { viterbi_fast_body<CODE, 2, 2>(p); }
+// soft / unquantized: one frame per thread, 32-bit keys
 template <class CODE>
 __global__ void __launch_bounds__(BD, 12) viterbi_fast_kernel_soft(const Params p) { viterbi_fast_body<CODE, 1, 1>(p); }
-// max |x| over a float buffer, as uint bits (non-negative floats order like unsigned ints)
-__global__ void absmax_kernel(const float *__restrict__ x, int64_t n, int clip500, uint32_t *out_bits)
+
+// Per-frame power-of-two scale for float input: the largest |value| of the frame (after the +-500 clip in 'soft'
+// mode, convcode.py:718-719; including the -1 padding of 'unquantized', :729-732) maps to at most 2^QBITS.
+// One warp per frame, coalesced; a frame's scale depends on nothing but the frame.
+__global__ void frame_scale_kernel(const float *__restrict__ x, int64_t n_in, int64_t n_used, int64_t batch, int mode,
+                                   float *__restrict__ scale)
 {
-    float m = 0.0f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float v = fabsf(x[i]);
+    const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= batch) return;
+    const int lane = threadIdx.x & 31;
+    const float *row = x + f * n_in;
+    float m = (mode == CPB_VITERBI_UNQUANTIZED) ? 1.0f : 0.0f;
+    auto take = [&](float v) {
+        v = fabsf(v);
         if (!(v <= 3.0e38f)) v = 3.0e38f;      // inf / nan
-        if (clip500) v = fminf(v, 500.0f);
+        if (mode == CPB_VITERBI_SOFT) v = fminf(v, 500.0f);
         m = fmaxf(m, v);
+    };
+    if ((n_in & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
+        const float4 *r4 = reinterpret_cast<const float4 *>(row);
+        const int64_t n4 = n_used >> 2;
+        for (int64_t i = lane; i < n4; i += 32) { const float4 v = __ldg(r4 + i); take(v.x); take(v.y); take(v.z); take(v.w); }
+        for (int64_t i = (n4 << 2) + lane; i < n_used; i += 32) take(__ldg(row + i));
+    } else {
+        for (int64_t i = lane; i < n_used; i += 32) take(__ldg(row + i));
     }
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));
+    if (lane == 0) {
+        m = fminf(fmaxf(m, 1e-30f), 3.0e38f);
+        float s = exp2f(floorf(log2f((float)QMAX / m)));
+        if (m * s > (float)QMAX) s *= 0.5f;     // log2f rounding at exact powers of two
+        scale[f] = fminf(s, 1.0e30f);
+    }
 }
 
 template <class CODE, int PACK>
 static int launch(const Params &p, cudaStream_t st)
 {
-    const size_t smem = smem_bytes(p.R, PACK);
+    const size_t smem = smem_bytes(p.RB, p.TBB, PACK);
     void (*kern)(const Params) = (PACK == 2) ? viterbi_fast_kernel_hard<CODE> : viterbi_fast_kernel_soft<CODE>;
-    CPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static thread_local size_t attr_set[64] = {0};       // per device: largest dynamic smem size already opted in
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (attr_set[dev] < smem) {
+        CPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dev] = smem;
+    }
     const int64_t grid = ceil_div(p.batch, (int64_t)BD * PACK);
     kern<<<(unsigned)grid, BD, smem, st>>>(p);
     CPB_LAUNCH_CHECK();
@@ -846,7 +905,7 @@ static bool use_fast(const cpbTrellis *t, int D, int mode, int in_dtype)
     // independent implementations can be compared against each other at full size (tests/test_viterbi_gpu.py)
     const char *force = getenv("CPB_VITERBI_FORCE_GENERIC");
     if (force && force[0] == '1') return false;
-    if (D < t->M + 1 || D > 48) return false;
+    if (D < t->M + 1 || D > fast::DMAX) return false;
     if (mode == CPB_VITERBI_HARD) return in_dtype == CPB_U8;
     return in_dtype == CPB_F32;
 }
@@ -882,7 +941,7 @@ int cpb_viterbi_workspace_bytes(const cpbTrellis *t, int64_t batch, int64_t n_in
     cpb_viterbi_sizes(t, n_in, &L, &T);
     const int D = resolve_depth(t, L, tb_depth);
     const int in_dtype = (mode == CPB_VITERBI_HARD) ? CPB_U8 : CPB_F32;
-    if (use_fast(t, D, mode, in_dtype)) { *bytes = 256; return CPB_OK; }
+    if (use_fast(t, D, mode, in_dtype)) { *bytes = 256 + (mode == CPB_VITERBI_HARD ? 0 : (size_t)batch * sizeof(float)); return CPB_OK; }
     int64_t stride;
     *bytes = generic_chunk(t, batch, T, &stride) + 256;
     return CPB_OK;
@@ -910,29 +969,28 @@ int cpb_viterbi_decode(const cpbTrellis *t, const void *coded_dev, int in_dtype,
         fast::Params p{};
         p.coded = coded_dev; p.n_in = n_in; p.batch = batch;
         p.L = (int)L; p.T = (int)T; p.D = D;
-        p.R = fast::TBB + D - 2 - (t->M - 1);
+        p.TBB = CPB_VITERBI_TBB;
+        p.NJ = (D > 8) ? (D - 8 + fast::B - 1) / fast::B : 0;
+        p.RB = p.NJ + p.TBB / fast::B;
         p.mode = mode; p.out = out_bits_dev;
-        p.out_vec16 = ((L % 16) == 0 && (((uintptr_t)out_bits_dev) % 16) == 0) ? 1 : 0;
-        Scratch ws;
-        int rc = ws.acquire(workspace_dev, workspace_bytes, 256, st);
-        if (rc) return rc;
+        p.out_vec8 = ((L % 8) == 0 && (((uintptr_t)out_bits_dev) % 8) == 0) ? 1 : 0;
         const int pack = (mode == CPB_VITERBI_HARD) ? 2 : 1;
-        if (fast::smem_bytes(p.R, pack) > dp.smem_optin) { ws.release(); return CPB_EUNSUPPORTED; }
-        p.keep_mask = (pack == 2) ? ~fast::KeyOps<2>::IDX_MASK : ~fast::KeyOps<1>::IDX_MASK;
-        p.sm_count = dp.sm_count > 0 ? dp.sm_count : 148;
-        {
-            const size_t row = (size_t)n_in * (pack == 2 ? 1 : 4), al = (pack == 2) ? 4 : 16;
-            p.in_aligned = ((n_in % 4) == 0 && (row % al) == 0 && (((uintptr_t)coded_dev) % al) == 0) ? 1 : 0;
-        }
+        const size_t need = 256 + (pack == 1 ? (size_t)batch * sizeof(float) : 0);
+        Scratch ws;
+        int rc = ws.acquire(workspace_dev, workspace_bytes, need, st);
+        if (rc) return rc;
+        if (fast::smem_bytes(p.RB, p.TBB, pack) > dp.smem_optin) { ws.release(); return CPB_EUNSUPPORTED; }
+        p.met_mask = (pack == 2) ? ~fast::KeyOps<2>::FMASK : ~fast::KeyOps<1>::FMASK;
+        if (pack == 2) p.in_aligned = ((n_in % 8) == 0 && (((uintptr_t)coded_dev) % 8) == 0) ? 1 : 0;
+        else p.in_aligned = ((n_in % 4) == 0 && (((uintptr_t)coded_dev) % 16) == 0) ? 1 : 0;
         if (pack == 1) {
-            p.amax_bits = reinterpret_cast<const uint32_t *>(ws.ptr);
-            cudaError_t e = cudaMemsetAsync(ws.ptr, 0, 4, st);
-            if (e != cudaSuccess) { ws.release(); return record_cuda_error(e, "cudaMemsetAsync", __FILE__, __LINE__); }
-            const int64_t nel = batch * n_in;
-            int g = (int)std::min<int64_t>(ceil_div(nel, 256 * 8), (int64_t)dp.sm_count * 16);
-            if (g < 1) g = 1;
-            fast::absmax_kernel<<<g, 256, 0, st>>>(reinterpret_cast<const float *>(coded_dev), nel,
-                                                    mode == CPB_VITERBI_SOFT, reinterpret_cast<uint32_t *>(ws.ptr));
+            float *sc = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(ws.ptr) + 256);
+            p.frame_scale = sc;
+            const int wpb = 8;
+            fast::frame_scale_kernel<<<(unsigned)ceil_div(batch, wpb), wpb * 32, 0, st>>>(
+                reinterpret_cast<const float *>(coded_dev), n_in, 2 * L, batch, mode, sc);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) { ws.release(); return record_cuda_error(e, "frame_scale_kernel", __FILE__, __LINE__); }
         }
         if (pack == 2) {
             if (t->fast_id == 1) rc = fast::launch<Code133_171, 2>(p, st);

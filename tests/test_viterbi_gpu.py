@@ -14,7 +14,7 @@ def _agree(got, want):
 
 
 @pytest.mark.parametrize("make", [helpers.k7, helpers.k7_wifi_quirk])
-@pytest.mark.parametrize("tb", [None, 15, 7, 48])
+@pytest.mark.parametrize("tb", [None, 15, 7, 46, 48])
 @pytest.mark.parametrize("term", ["cont", "term"])
 def test_k7_hard_bit_exact(make, tb, term):
     tr = make()
@@ -156,10 +156,58 @@ def test_edge_cases_sizes_and_alignment():
                     assert (got == want).mean() >= 0.999, (mode, batch, nbits)
     # smallest depth (generic kernel: D = 2) and the largest the fast path takes (48), device-resident unaligned view
     _, x = helpers.channel_frames(tr, rs, 9, 200, "hard", "cont", flip=0.05)
-    for tb in (2, 3, 6, 48, 49, 120):
+    for tb in (2, 3, 6, 8, 9, 10, 11, 12, 13, 46, 47, 48, 49, 120):
         assert np.array_equal(viterbi_decode_batch(x.astype(np.uint8), tr, tb, "hard"),
                               oracle.viterbi_decode_batch(x, tr, tb, "hard")), tb
+    # deepest fast-path depth with a final block that is exactly full (L = 17 mod 24), every frame length
+    # modulo the 4-step history block and the 24-window traceback block
+    for nbits in (65, 185, 209, 64, 66, 67, 88, 89, 90, 91):
+        _, xx = helpers.channel_frames(tr, rs, 5, nbits, "hard", "cont", flip=0.08)
+        for tb in (None, 46, 48, 7, 8):
+            assert np.array_equal(viterbi_decode_batch(xx.astype(np.uint8), tr, tb, "hard"),
+                                  oracle.viterbi_decode_batch(xx, tr, tb, "hard")), (nbits, tb)
     big = torch.from_numpy(np.concatenate([np.zeros((9, 3)), x], axis=1).astype(np.uint8)).cuda()
     view = big[:, 3:]                                # non-contiguous view: the wrapper must densify it
     assert np.array_equal(viterbi_decode_batch(view, tr, None, "hard").cpu().numpy(),
                           oracle.viterbi_decode_batch(x, tr, None, "hard"))
+
+
+@pytest.mark.parametrize("mode", ["soft", "unquantized"])
+def test_float_decode_is_batch_invariant(mode):
+    """a frame's decode must not depend on what it is batched with.  (a) one outlier frame (huge
+    values, +-inf) in the batch leaves every other frame's output unchanged; (b) frames [0, B) in one call equal two calls
+    of B/2; (c) the outlier frame itself still decodes like the oracle."""
+    import torch
+    tr = helpers.k7()
+    rs = np.random.RandomState(21)
+    msgs, x = helpers.channel_frames(tr, rs, 96, 512, mode, "cont", ebn0_db=3.0)
+    x = x.astype(np.float32)
+    base = viterbi_decode_batch(x, tr, None, mode)
+    xo = x.copy()
+    xo[17] *= 1.0e6
+    if mode == "soft":
+        xo[40, ::7] = np.inf
+        xo[40, 3::7] = -np.inf
+    got = viterbi_decode_batch(xo, tr, None, mode)
+    keep = np.ones(96, bool)
+    keep[[17, 40]] = False
+    assert np.array_equal(got[keep], base[keep])
+    want = oracle.viterbi_decode_batch(xo[[17, 40]].astype(np.float64), tr, None, mode)
+    assert (got[[17, 40]] == want).mean() >= 0.995
+    xt = torch.from_numpy(x).cuda()
+    full = viterbi_decode_batch(xt, tr, None, mode)
+    h0 = viterbi_decode_batch(xt[:48].contiguous(), tr, None, mode)
+    h1 = viterbi_decode_batch(xt[48:].contiguous(), tr, None, mode)
+    assert torch.equal(full, torch.cat([h0, h1]))
+    assert np.array_equal(full.cpu().numpy(), base)
+
+
+def test_c2_shape_soft_vs_oracle():
+    """BASELINE config 2 shape: K=7 soft-decision, N=4096, AWGN Eb/N0 = 4 dB: 64 frames against the fp64 oracle."""
+    tr = helpers.k7()
+    rs = np.random.RandomState(22)
+    msgs, x = helpers.channel_frames(tr, rs, 64, 4096, "soft", "cont", ebn0_db=4.0)
+    want = oracle.viterbi_decode_batch(x, tr, None, "soft", threads=8)
+    got = viterbi_decode_batch(x.astype(np.float32), tr, None, "soft")
+    assert (got != want).mean() <= 1e-4
+    assert abs(int((got != msgs).sum()) - int((want != msgs).sum())) <= 8
