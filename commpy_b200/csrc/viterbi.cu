@@ -121,7 +121,7 @@ struct Params {
     const float *frame_scale;    // float input: power-of-two scale per frame (device)
     uint8_t *out;
     int out_vec8;                // 1: rows of out are 8-byte aligned
-    int in_aligned;              // 1: rows of coded are 8-byte (u8) / 16-byte (f32) aligned
+    int in_aligned;              // 1: rows of coded are 4-byte (u8) / 16-byte (f32) aligned
     uint32_t met_mask;           // metric bits of a key, passed at run time so the key refresh stays one LOP3
 };
 
@@ -175,26 +175,28 @@ __device__ __forceinline__ uint32_t acs_step(const uint32_t (&K)[64], uint32_t (
     return OPS::min3(a, b, OPS::min2(q[6], q[7]));
 }
 
-// shared memory of one warp-CTA
+// shared memory of one warp-CTA (byte offsets into smem_raw, so every access below compiles to LDS / STS / ATOMS)
+extern __shared__ __align__(16) unsigned char smem_raw[];
 template <int PACK>
 struct Smem {
     static constexpr int NW = 8 * PACK;     // 32-bit words of jump nibbles per block and thread
-    uint32_t *nib;      // jump nibbles [RB][NW][32]: word w = states 4w..4w+3 (frame A low half, B high half) when
-                        // PACK = 2, states 8w..8w+7 when PACK = 1
-    uint32_t *bf;       // best fields of the running traceback block [TBB][32] (frame B in the high half)
-    uint4 *lut;         // hard-decision branch metrics [16]
-    uint32_t *tasks;    // retired-path tasks [2*TASK_CAP]
-    uint32_t *ntasks;   // [1]
-    uint32_t *outbits;  // [32*PACK]
+    int nib;        // jump nibbles [RB][NW][32] u32: word w = states 4w..4w+3 (frame A low half, B high half) when
+                    // PACK = 2, states 8w..8w+7 when PACK = 1
+    int bf;         // best fields of the running traceback block [TBB/4][32] uint4 (one component per sub-step,
+                    // frame B in the high half)
+    int lut;        // hard-decision branch metrics [16] uint4
+    int tasks;      // retired-path tasks [TASK_CAP] uint2
+    int outbits;    // [32*PACK] u32
     int RB;
 };
+template <typename T> __device__ __forceinline__ T &sm_at(int off) { return *reinterpret_cast<T *>(smem_raw + off); }
 
 static size_t smem_bytes(int RB, int TBB, int pack)
 {
     size_t b = (size_t)RB * 8 * pack * BD * sizeof(uint32_t);
     b += (size_t)TBB * BD * sizeof(uint32_t);
     b += 16 * sizeof(uint4);
-    b += (size_t)2 * TASK_CAP * sizeof(uint32_t) + 16;
+    b += (size_t)2 * TASK_CAP * sizeof(uint32_t);
     b += (size_t)BD * pack * sizeof(uint32_t);
     return b;
 }
@@ -203,126 +205,57 @@ static size_t smem_bytes(int RB, int TBB, int pack)
 template <int PACK, typename PT>
 struct Jumper {
     static constexpr int ROWB = 8 * PACK * BD * 4;      // bytes per ring block
-    const unsigned char *nbase;
-    int rowoff, wrap, colsh, fish;
+    int base, rowoff, wrap, fish;                       // base = ring offset + 4 * column
     PT reg;
     __device__ __forceinline__ void init(const Smem<PACK> &sm, int slot, int col, int fi, PT r0)
     {
-        nbase = reinterpret_cast<const unsigned char *>(sm.nib);
-        rowoff = slot * ROWB; wrap = sm.RB * ROWB; colsh = col * 4; fish = 16 * fi; reg = r0;
+        base = sm.nib + col * 4; rowoff = slot * ROWB; wrap = sm.RB * ROWB; fish = 16 * fi; reg = r0;
     }
     __device__ __forceinline__ void jump()
     {
         const uint32_t st = (uint32_t)reg & 63u;
         const int wsel = (PACK == 2) ? (int)((st >> 2) << 7) : (int)((st >> 3) << 7);
         const uint32_t sh = (PACK == 2) ? (((st & 3u) << 2) | (uint32_t)fish) : ((st & 7u) << 2);
-        const uint32_t word = *reinterpret_cast<const uint32_t *>(nbase + rowoff + wsel + colsh);
+        const uint32_t word = sm_at<uint32_t>(base + rowoff + wsel);
         reg = (PT)(reg << B) | (PT)((word >> sh) & 15u);
         rowoff -= ROWB;
         if (rowoff < 0) rowoff += wrap;
     }
 };
 
-// Traceback of the windows tau in (ts, te] (App. A.1-8): output bit p = tau - D + 1 is the input u_{tau-D+2} on the
-// survivor path that starts at best[tau]  (ts is a block boundary; te = ts + TBB, or T in the final block).
-//   phase A  every thread walks tau = te .. ts+1 once along the current path of each of its frames (one look-up per
-//            B steps); where the path misses best[tau] it is retired into a task (it still owes the bits of the
-//            windows (tau, hi] it served) and a new path starts from the field of best[tau].
-//   phase B  every retired path needs NJ more jumps; any lane can run any task (the ring is in shared memory), so
-//            the warp shares them evenly, two per lane at a time.
-// A path that served the windows (lo, hi], was retired in the block above boundary t0s and has been jumped NJ times
-// holds block bit k (window ts+1+k) at register bit k + shc - (t0s - ts), shc = 4*NJ - D + 8 in [0, 3].
-// In the final block the path from best[T] also owns every later bit up to L-1 (a separate 64-bit walk).
-template <class CODE, int PACK, bool FINAL>
-__device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int te, int slot_last, int D, int L, int NJ,
-                                               uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec8)
+// block bits of a path: it served the windows (lo, hi] and was retired in the block above boundary ts + delta
+__device__ __forceinline__ uint32_t tb_contribution(uint32_t reg, int delta, int lo, int hi, int ts, int shc)
+{
+    uint32_t v = (reg << delta) >> shc;
+    v &= ~0u << (lo - ts);
+    v &= ~(~0u << (hi - ts));
+    return v;
+}
+
+// phase B of the traceback: every queued retired path needs NJ more jumps; any lane can run any task (the ring is in
+// shared memory), so the warp shares them evenly, two per lane at a time
+template <int PACK>
+__device__ __noinline__ void tb_run_tasks(const Smem<PACK> sm, int ntask, int ts, int NJ, int shc)
 {
     const int lane = threadIdx.x;
-    const int p0 = ts - D + 2;                          // output bit of window ts+1
-    const int shc = 4 * NJ - D + 8;
-    const int jte = (te - 1) & 3;
-    // ring slot of the block that ended at the boundary below te
-    int bslot0 = slot_last;
-    if (jte == 3) bslot0 = (slot_last == 0) ? sm.RB - 1 : slot_last - 1;
-    auto contribution = [&](uint32_t reg, int delta, int lo, int hi) -> uint32_t {
-        uint32_t v = (reg << delta) >> shc;
-        v &= ~0u << (lo - ts);
-        v &= ~(~0u << (hi - ts));
-        return v;
-    };
-    if (lane == 0) *sm.ntasks = 0u;
-    uint32_t acc[PACK];
-    int hi[PACK];
-    Jumper<PACK, uint32_t> jw[PACK];
-    const uint32_t bwe = sm.bf[(te - ts - 1) * BD + lane];
-#pragma unroll
-    for (int fi = 0; fi < PACK; ++fi) {
-        acc[fi] = 0; hi[fi] = te;
-        jw[fi].init(sm, bslot0, lane, fi, (bwe >> (16 * fi)) & 0x3FFu);
-        sm.outbits[lane + BD * fi] = 0u;
-    }
     __syncwarp();
-    // ---- phase A
-    for (int tau = te - 1; tau > ts; --tau) {
-        const int j = (tau - 1) & 3;
-        if (j == 3) {
-#pragma unroll
-            for (int fi = 0; fi < PACK; ++fi) jw[fi].jump();
-        }
-        const uint32_t bw = sm.bf[(tau - ts - 1) * BD + lane];
-        const uint32_t msk = 63u << (j + 1);
-#pragma unroll
-        for (int fi = 0; fi < PACK; ++fi) {
-            const uint32_t b = (bw >> (16 * fi)) & 0x3FFu;
-            if (tau < hi[fi] && ((jw[fi].reg ^ b) & msk)) {     // the path does not pass through best[tau]: retire it
-                const uint32_t qi = atomicAdd(sm.ntasks, 1u);
-                const int delta = tau - 1 - j - ts;             // boundary below tau, relative to ts (multiple of 4)
-                if (qi < (uint32_t)TASK_CAP) {
-                    sm.tasks[2 * qi] = (uint32_t)lane | ((uint32_t)fi << 5) |
-                                       ((uint32_t)(jw[fi].rowoff / Jumper<PACK, uint32_t>::ROWB) << 6) |
-                                       ((uint32_t)(tau - ts) << 12) | ((uint32_t)(hi[fi] - ts) << 17) |
-                                       ((uint32_t)(delta >> 2) << 22);
-                    sm.tasks[2 * qi + 1] = jw[fi].reg;
-                } else {
-                    Jumper<PACK, uint32_t> t = jw[fi];
-                    for (int i = 0; i < NJ; ++i) t.jump();
-                    acc[fi] |= contribution(t.reg, delta, tau, hi[fi]);
-                }
-                hi[fi] = tau;
-                jw[fi].reg = b;
-            }
-        }
-    }
-    // ---- closing paths of this thread's own frames (interleaved for ILP); the walk above ended at boundary ts
-    if (te - ts > 1 || true) {
-        // after the loop the jumpers stand at the boundary below ts+1, which is ts itself unless te == ts+1..ts+3 in a
-        // final block that never left its first block: in every case the boundary is ts (te > ts, blocks are aligned)
-    }
-    for (int i = 0; i < NJ; ++i) {
-#pragma unroll
-        for (int fi = 0; fi < PACK; ++fi) jw[fi].jump();
-    }
-#pragma unroll
-    for (int fi = 0; fi < PACK; ++fi) acc[fi] |= contribution(jw[fi].reg, 0, ts, hi[fi]);
-    __syncwarp();
-    // ---- phase B: retired paths, two per lane at a time
-    int ntasks = (int)*sm.ntasks;
-    if (ntasks > TASK_CAP) ntasks = TASK_CAP;
-    for (int base = 0; base < ntasks; base += 2 * BD) {
+    for (int base = 0; base < ntask; base += 2 * BD) {
         Jumper<PACK, uint32_t> tw[2];
         int lo[2], thi[2], dst[2], dl[2];
         bool on[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int i = base + u * BD + lane;
-            on[u] = i < ntasks;
-            const uint32_t a = on[u] ? sm.tasks[2 * i] : 0u;
+            on[u] = i < ntask;
+            const uint2 tk = on[u] ? sm_at<uint2>(sm.tasks + i * 8) : make_uint2(0u, 0u);
+            const uint32_t a = tk.x;
             const int col = a & 31, fi = (a >> 5) & 1;
             lo[u] = ts + (int)((a >> 12) & 31u); thi[u] = ts + (int)((a >> 17) & 31u);
             dl[u] = (int)((a >> 22) & 15u) << 2;
-            dst[u] = col + BD * fi;
-            tw[u].init(sm, (int)((a >> 6) & 63u), col, fi, on[u] ? sm.tasks[2 * i + 1] : 0u);
+            dst[u] = sm.outbits + (col + BD * fi) * 4;
+            tw[u].init(sm, (int)((a >> 6) & 63u), col, fi, tk.y);
         }
+#pragma unroll 1
         for (int i = 0; i < NJ; ++i) {
 #pragma unroll
             for (int u = 0; u < 2; ++u) tw[u].jump();
@@ -330,18 +263,107 @@ __device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int t
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             if (!on[u]) continue;
-            const uint32_t bits = contribution(tw[u].reg, dl[u], lo[u], thi[u]);
-            if (bits) atomicOr(&sm.outbits[dst[u]], bits);
+            const uint32_t bits = tb_contribution(tw[u].reg, dl[u], lo[u], thi[u], ts, shc);
+            if (bits) atomicOr(&sm_at<uint32_t>(dst[u]), bits);
         }
     }
     __syncwarp();
+}
+
+// Traceback of the windows tau in (ts, te] (App. A.1-8): output bit p = tau - D + 1 is the input u_{tau-D+2} on the
+// survivor path that starts at best[tau]  (ts is a block boundary; te = ts + TBB, or T in the final block).
+//   phase A  every thread walks tau = te .. ts+1 once along the current path of each of its frames (one look-up per
+//            B steps); where the path misses best[tau] it is retired into a task (it still owes the bits of the
+//            windows (tau, hi] it served) and a new path starts from the field of best[tau].  The whole warp walks in
+//            lock step, so task slots come from a ballot -- no atomics.
+//   phase B  every retired path needs NJ more jumps; any lane can run any task (the ring is in shared memory), so
+//            the warp shares them evenly, two per lane at a time.
+// A path that served the windows (lo, hi], was retired in the block above boundary t0s and has been jumped NJ times
+// holds block bit k (window ts+1+k) at register bit k + shc - (t0s - ts), shc = 4*NJ - D + 8 in [0, 3].
+// In the final block the path from best[T] also owns every later bit up to L-1 (a separate 64-bit walk).
+template <class CODE, int PACK>
+__device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int te, int slot_last, int D, int L, int NJ,
+                                               uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec8, bool final)
+{
+    const int lane = threadIdx.x;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int p0 = ts - D + 2;                          // output bit of window ts+1
+    const int shc = 4 * NJ - D + 8;
+    const int jte = (te - 1) & 3;
+    // ring slot of the block that ended at the boundary below te
+    int bslot0 = slot_last;
+    if (jte == 3) bslot0 = (slot_last == 0) ? sm.RB - 1 : slot_last - 1;
+    uint32_t acc[PACK];
+    int hi[PACK];
+    Jumper<PACK, uint32_t> jw[PACK];
+    int ntask = 0;                                      // warp-uniform
+    // best fields of the block that holds te
+    int bfo = sm.bf + (((te - 1 - ts) >> 2) * BD + lane) * 16;
+    uint4 bq = sm_at<uint4>(bfo);
+    const uint32_t bwe = (jte == 0) ? bq.x : (jte == 1) ? bq.y : (jte == 2) ? bq.z : bq.w;
 #pragma unroll
     for (int fi = 0; fi < PACK; ++fi) {
-        const uint32_t a32 = acc[fi] | sm.outbits[lane + BD * fi];
+        hi[fi] = te;
+        jw[fi].init(sm, bslot0, lane, fi, (bwe >> (16 * fi)) & 0x3FFu);
+        sm_at<uint32_t>(sm.outbits + (lane + BD * fi) * 4) = 0u;
+    }
+    // one window: does the current path of frame fi pass through best[tau]?  (j = sub-step of tau, bw = best fields)
+    // Branch free: the task slot comes from a ballot, the store and the path switch are predicated.
+    auto check = [&](int tau, int j, uint32_t bw) {
+        const uint32_t msk = 63u << (j + 1);
+        const uint32_t twc = (uint32_t)lane | ((uint32_t)(tau - ts) << 12) | ((uint32_t)((tau - 1 - j - ts) >> 2) << 22);
+        if (__builtin_expect(ntask > TASK_CAP - 2 * BD, 0)) {    // (warp-uniform, rare) queue nearly full: drain it
+            tb_run_tasks<PACK>(sm, ntask, ts, NJ, shc);
+            ntask = 0;
+        }
+#pragma unroll
+        for (int fi = 0; fi < PACK; ++fi) {
+            const uint32_t b = (bw >> (16 * fi)) & 0x3FFu;
+            const bool miss = ((jw[fi].reg ^ b) & msk) != 0u;
+            const uint32_t vote = __ballot_sync(0xffffffffu, miss);
+            const int qi = ntask + __popc(vote & lt_mask);
+            ntask += __popc(vote);
+            if (miss)                                            // retire the path: it served the windows (tau, hi]
+                sm_at<uint2>(sm.tasks + qi * 8) = make_uint2(
+                    twc | ((uint32_t)fi << 5) | (((uint32_t)jw[fi].rowoff / (uint32_t)Jumper<PACK, uint32_t>::ROWB) << 6) |
+                        ((uint32_t)(hi[fi] - ts) << 17),
+                    jw[fi].reg);
+            hi[fi] = miss ? tau : hi[fi];
+            jw[fi].reg = miss ? b : jw[fi].reg;
+        }
+    };
+    // ---- phase A: the rest of the block that holds te, then whole blocks down to ts
+    int tau = te - 1;
+    for (int j = jte - 1; j >= 0; --j, --tau)
+        check(tau, j, (j == 0) ? bq.x : (j == 1) ? bq.y : bq.z);
+    while (tau > ts) {
+#pragma unroll
+        for (int fi = 0; fi < PACK; ++fi) jw[fi].jump();
+        bfo -= BD * 16;
+        bq = sm_at<uint4>(bfo);
+        check(tau, 3, bq.w);
+        check(tau - 1, 2, bq.z);
+        check(tau - 2, 1, bq.y);
+        check(tau - 3, 0, bq.x);
+        tau -= 4;
+    }
+    // ---- closing paths of this thread's own frames (interleaved for ILP); the walk above ended at boundary ts
+#pragma unroll 1
+    for (int i = 0; i < NJ; ++i) {
+#pragma unroll
+        for (int fi = 0; fi < PACK; ++fi) jw[fi].jump();
+    }
+#pragma unroll
+    for (int fi = 0; fi < PACK; ++fi) acc[fi] = tb_contribution(jw[fi].reg, 0, ts, hi[fi], ts, shc);
+    // ---- phase B: the retired paths
+    tb_run_tasks<PACK>(sm, ntask, ts, NJ, shc);
+#pragma unroll
+    for (int fi = 0; fi < PACK; ++fi) {
+        const uint32_t a32 = acc[fi] | sm_at<uint32_t>(sm.outbits + (lane + BD * fi) * 4);
         if (!((valid_mask >> fi) & 1)) continue;
         uint8_t *orow = (fi == 0 ? out0 : out1);
         const int nbw = te - ts;
-        if (!FINAL && out_vec8 && p0 >= 0 && (p0 & 7) == 0 && (nbw & 7) == 0) {
+        if (out_vec8 && p0 >= 0 && (p0 & 7) == 0 && (nbw & 7) == 0) {
             // 8 decoded bits -> 8 bytes per store
             for (int g8 = 0; g8 < nbw; g8 += 8) {
                 const uint32_t b8 = (a32 >> g8) & 0xffu;
@@ -354,10 +376,11 @@ __device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int t
             for (int i = 0; i < nbw; ++i)
                 if (p0 + i >= 0) orow[p0 + i] = (uint8_t)((a32 >> i) & 1u);
         }
-        if (FINAL) {
+        if (final) {
             // the path from best[T] decides every bit from T-D+2 on (u_{T-D+3} .. u_{T-5}): D-7 bits
             Jumper<PACK, unsigned long long> t;
             t.init(sm, bslot0, lane, fi, (unsigned long long)((bwe >> (16 * fi)) & 0x3FFu));
+#pragma unroll 1
             for (int i = 0; i < NJ; ++i) t.jump();
             const unsigned long long tail = t.reg >> (jte + 1 + shc);
             const int pt = te - D + 2;
@@ -369,26 +392,35 @@ __device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int t
 
 // the traceback is a call in the hard kernel (its 64 packed keys stay in callee-saved registers) and inlined in the
 // register-capped soft kernel (CPB_TB_INLINE_SOFT)
-template <class CODE, int PACK, bool FINAL>
+template <class CODE, int PACK>
 __device__ __noinline__ void tb_block_call(const Smem<PACK> sm, int ts, int te, int slot_last, int D, int L, int NJ,
-                                           uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec8)
+                                           uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec8, bool final)
 {
-    tb_block_body<CODE, PACK, FINAL>(sm, ts, te, slot_last, D, L, NJ, out0, out1, valid_mask, out_vec8);
+    tb_block_body<CODE, PACK>(sm, ts, te, slot_last, D, L, NJ, out0, out1, valid_mask, out_vec8, final);
 }
+#ifndef CPB_QD_HARD
+#define CPB_QD_HARD 4              // input prefetch distance of the hard kernel, in pairs of steps
+#endif
+#ifndef CPB_TB_DEPHASE
+#define CPB_TB_DEPHASE 8           // windows in the first traceback block of the second warp of a scheduler (0: off)
+#endif
 #ifndef CPB_TB_INLINE_SOFT
 #define CPB_TB_INLINE_SOFT 1
 #endif
 #ifndef CPB_TB_INLINE_HARD
 #define CPB_TB_INLINE_HARD 0
 #endif
-template <class CODE, int PACK, bool FINAL>
+template <class CODE, int PACK>
 __device__ __forceinline__ void tb_block(const Smem<PACK> sm, int ts, int te, int slot_last, int D, int L, int NJ,
-                                         uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec8)
+                                         uint8_t *out0, uint8_t *out1, int valid_mask, int out_vec8, bool final)
 {
+#ifdef CPB_EXP_NO_TB          // experiment: add-compare-select only (wrong output)
+    if (!final) return;
+#endif
     if ((PACK == 1 && CPB_TB_INLINE_SOFT) || (PACK == 2 && CPB_TB_INLINE_HARD))
-        tb_block_body<CODE, PACK, FINAL>(sm, ts, te, slot_last, D, L, NJ, out0, out1, valid_mask, out_vec8);
+        tb_block_body<CODE, PACK>(sm, ts, te, slot_last, D, L, NJ, out0, out1, valid_mask, out_vec8, final);
     else
-        tb_block_call<CODE, PACK, FINAL>(sm, ts, te, slot_last, D, L, NJ, out0, out1, valid_mask, out_vec8);
+        tb_block_call<CODE, PACK>(sm, ts, te, slot_last, D, L, NJ, out0, out1, valid_mask, out_vec8, final);
 }
 
 template <class CODE, int PACK, int QD>
@@ -398,18 +430,16 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
     constexpr int S = CODE::S, M = CODE::M;
     constexpr int NW = 8 * PACK;
     static_assert(S == 64 && M == 6, "fast path is written for 64 states");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     Smem<PACK> sm;
     {
-        unsigned char *q = smem_raw;
+        int q = 0;
         sm.RB = p.RB;
-        sm.nib = reinterpret_cast<uint32_t *>(q); q += (size_t)p.RB * NW * BD * sizeof(uint32_t);
-        sm.bf = reinterpret_cast<uint32_t *>(q); q += (size_t)p.TBB * BD * sizeof(uint32_t);
-        sm.lut = reinterpret_cast<uint4 *>(q); q += 16 * sizeof(uint4);
-        sm.tasks = reinterpret_cast<uint32_t *>(q); q += (size_t)2 * TASK_CAP * sizeof(uint32_t);
-        sm.ntasks = reinterpret_cast<uint32_t *>(q); q += 16;
-        sm.outbits = reinterpret_cast<uint32_t *>(q);
+        sm.nib = q; q += p.RB * NW * BD * (int)sizeof(uint32_t);
+        sm.bf = q; q += p.TBB * BD * (int)sizeof(uint32_t);
+        sm.lut = q; q += 16 * (int)sizeof(uint4);
+        sm.tasks = q; q += 2 * TASK_CAP * (int)sizeof(uint32_t);
+        sm.outbits = q;
     }
     if (PACK == 2) {
         // hard-decision branch metrics of two frames: entry idx = r0A | r1A<<1 | r0B<<2 | r1B<<3,
@@ -418,7 +448,7 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
             const int a = ((tid & 1) << 1) | ((tid >> 1) & 1), b = (((tid >> 2) & 1) << 1) | ((tid >> 3) & 1);
             uint32_t e[4];
             for (int o = 0; o < 4; ++o) e[o] = ((uint32_t)__popc(o ^ a) << FB) | ((uint32_t)__popc(o ^ b) << (16 + FB));
-            sm.lut[tid] = make_uint4(e[0], e[1], e[2], e[3]);
+            sm_at<uint4>(sm.lut + tid * 16) = make_uint4(e[0], e[1], e[2], e[3]);
         }
         __syncwarp();
     }
@@ -458,45 +488,43 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
 
     const unsigned char *c8 = reinterpret_cast<const unsigned char *>(p.coded);
     const float *cf = reinterpret_cast<const float *>(p.coded);
-    const int nblk_in = p.L >> 2;                // blocks of B steps fully covered by received data
+    const int npairs_in = p.L >> 1;              // pairs of steps fully covered by received data
 
-    // raw received values of the B steps of block blk (steps 4 blk + 1 .. 4 blk + 4)
-    struct Raw { uint32_t w[(PACK == 2) ? 4 : 8]; };
-    auto load_block = [&](int blk) {
+    // received values of the pair of steps (2 pr + 1, 2 pr + 2)
+    //   hard: the 4 coded bytes of frame A and of frame B;  float: the 4 raw values
+    struct Raw { uint32_t w[(PACK == 2) ? 2 : 4]; };
+    auto load_pair = [&](int pr) {
         Raw r;
         if (PACK == 2) {
-            // w[0..1] = the 8 coded bytes of frame A, w[2..3] = frame B; past the data: zeros (convcode.py:727-728)
-            r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0u;
-            if (p.in_aligned && blk < nblk_in) {
-                const uint2 a = __ldg(reinterpret_cast<const uint2 *>(c8 + fr[0] * p.n_in) + blk);
-                const uint2 b = __ldg(reinterpret_cast<const uint2 *>(c8 + fr[PACK - 1] * p.n_in) + blk);
-                r.w[0] = a.x; r.w[1] = a.y; r.w[2] = b.x; r.w[3] = b.y;
+            // a = the 4 coded bytes of frame A, b = frame B; past the data: zeros (convcode.py:727-728)
+            uint32_t a = 0u, b = 0u;
+            if (p.in_aligned && pr < npairs_in) {
+                a = __ldg(reinterpret_cast<const uint32_t *>(c8 + fr[0] * p.n_in) + pr);
+                b = __ldg(reinterpret_cast<const uint32_t *>(c8 + fr[PACK - 1] * p.n_in) + pr);
             } else {
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const int tau = 4 * blk + 1 + h;
+                for (int h = 0; h < 2; ++h) {
+                    const int tau = 2 * pr + 1 + h;
                     if (tau <= p.L) {
                         const unsigned char *qa = c8 + fr[0] * p.n_in + 2 * (int64_t)(tau - 1);
                         const unsigned char *qb = c8 + fr[PACK - 1] * p.n_in + 2 * (int64_t)(tau - 1);
-                        r.w[h >> 1] |= ((uint32_t)__ldg(qa) | ((uint32_t)__ldg(qa + 1) << 8)) << (16 * (h & 1));
-                        r.w[2 + (h >> 1)] |= ((uint32_t)__ldg(qb) | ((uint32_t)__ldg(qb + 1) << 8)) << (16 * (h & 1));
+                        a |= ((uint32_t)__ldg(qa) | ((uint32_t)__ldg(qa + 1) << 8)) << (16 * h);
+                        b |= ((uint32_t)__ldg(qb) | ((uint32_t)__ldg(qb + 1) << 8)) << (16 * h);
                     }
                 }
             }
+            r.w[0] = a; r.w[1] = b;         // (nothing is computed here: the queue must not wait for the load)
         } else {
             const uint32_t pb = __float_as_uint(padq);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) r.w[i] = pb;
+            r.w[0] = r.w[1] = r.w[2] = r.w[3] = pb;
             const float *row = cf + fr[0] * p.n_in;
-            if (p.in_aligned && blk < nblk_in) {
-                const float4 v0 = __ldg(reinterpret_cast<const float4 *>(row) + 2 * blk);
-                const float4 v1 = __ldg(reinterpret_cast<const float4 *>(row) + 2 * blk + 1);
-                r.w[0] = __float_as_uint(v0.x); r.w[1] = __float_as_uint(v0.y); r.w[2] = __float_as_uint(v0.z); r.w[3] = __float_as_uint(v0.w);
-                r.w[4] = __float_as_uint(v1.x); r.w[5] = __float_as_uint(v1.y); r.w[6] = __float_as_uint(v1.z); r.w[7] = __float_as_uint(v1.w);
+            if (p.in_aligned && pr < npairs_in) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(row) + pr);
+                r.w[0] = __float_as_uint(v.x); r.w[1] = __float_as_uint(v.y); r.w[2] = __float_as_uint(v.z); r.w[3] = __float_as_uint(v.w);
             } else {
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const int tau = 4 * blk + 1 + h;
+                for (int h = 0; h < 2; ++h) {
+                    const int tau = 2 * pr + 1 + h;
                     if (tau <= p.L) {
                         r.w[2 * h] = __float_as_uint(__ldg(row + 2 * (int64_t)(tau - 1)));
                         r.w[2 * h + 1] = __float_as_uint(__ldg(row + 2 * (int64_t)(tau - 1) + 1));
@@ -506,12 +534,20 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
         }
         return r;
     };
-    // the four branch metrics (in the metric field) of sub-step h of a block
+    // hard: the 4 received bits of a step (two frames) are gathered into one nibble by two multiplies.  Bytes (r0, r1 of
+    // step a, r0, r1 of step b), each 0/1 -> bits (0,1,4,5) [frame A] / (2,3,6,7) [frame B] of the top byte: term
+    // 2^(24-8i+pos_i) moves byte i to bit 24+pos_i, every stray product lands on its own lower bit (no carries).
+    // Byte (w >> 24) = table index of step a | table index of step b << 4.
+    auto gather = [&](const Raw &r) {
+        Raw g = r;
+        if (PACK == 2) g.w[0] = (r.w[0] & 0x01010101u) * 0x01021020u + (r.w[1] & 0x01010101u) * 0x04084080u;
+        return g;
+    };
+    // the four branch metrics (in the metric field) of step h (0 / 1) of a (gathered) pair
     auto make_bm = [&](const Raw &r, int h, uint32_t (&Bm)[4]) {
         if (PACK == 2) {
-            const uint32_t wa = r.w[h >> 1], wb = r.w[2 + (h >> 1)];
-            const uint32_t ta = (wa | (wa >> 7)) >> (16 * (h & 1)), tb = (wb | (wb >> 7)) >> (16 * (h & 1));
-            const uint4 e = sm.lut[(ta & 3u) | ((tb & 3u) << 2)];
+            const uint32_t off = (r.w[0] >> (h ? 24 : 20)) & 0xF0u;      // 16 * table index
+            const uint4 e = sm_at<uint4>(sm.lut + (int)off);
             Bm[0] = e.x; Bm[1] = e.y; Bm[2] = e.z; Bm[3] = e.w;
         } else {
             float r0 = __uint_as_float(r.w[2 * h]), r1 = __uint_as_float(r.w[2 * h + 1]);
@@ -532,18 +568,26 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
     const int ts0 = (p.D - 2) & ~3;              // first traceback block starts at this boundary (windows exist from D-1)
     int ts_cur = ts0;
     int next_te = ts_cur + p.TBB;
+    if (CPB_TB_DEPHASE) {
+        // The traceback is latency bound, the add-compare-select loop pipe bound: two warps that share a scheduler
+        // (hardware warp slots w and w+4) should not trace back at the same time, so the second one ends its first
+        // traceback block half a period early.  (Scheduling only: the output does not depend on the block boundaries.)
+        uint32_t wid;
+        asm("mov.u32 %0, %%warpid;" : "=r"(wid));
+        if ((wid >> 2) & 1u) next_te = ts_cur + CPB_TB_DEPHASE;   // a multiple of 8: output stores stay 8-byte aligned
+    }
     int nslot = 0;                               // ring slot the next completed block goes to
-    const int nfull = p.T >> 2, rem = p.T & 3;
 
     // end of a block of B steps (keys in Kc, mn = minimum key of the last step): jump nibbles to the ring, keys back to
     // metric | state, renormalisation
     auto block_end = [&](uint32_t (&Kc)[64], uint32_t mn, int tau) {
+        const int nb = sm.nib + (nslot * NW * BD + tid) * 4;
         if (PACK == 2) {
 #pragma unroll
             for (int w = 0; w < 16; ++w) {
                 const uint32_t t0 = (Kc[4 * w] & OPS::NIBM) | ((Kc[4 * w + 1] << 4) & ~OPS::NIBM);
                 const uint32_t t1 = (Kc[4 * w + 2] & OPS::NIBM) | ((Kc[4 * w + 3] << 4) & ~OPS::NIBM);
-                sm.nib[(nslot * NW + w) * BD + tid] = __byte_perm(t0, t1, 0x6240);
+                sm_at<uint32_t>(nb + w * BD * 4) = __byte_perm(t0, t1, 0x6240);
             }
         } else {
 #pragma unroll
@@ -552,82 +596,93 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     t[i] = (Kc[8 * w + 2 * i] & OPS::NIBM) | ((Kc[8 * w + 2 * i + 1] << 4) & ~OPS::NIBM);
-                sm.nib[(nslot * NW + w) * BD + tid] =
+                sm_at<uint32_t>(nb + w * BD * 4) =
                     __byte_perm(__byte_perm(t[0], t[1], 0x0040), __byte_perm(t[2], t[3], 0x0040), 0x5410);
             }
         }
-        const bool renorm = (PACK == 1) || ((tau & 7) == 0);
-        const uint32_t sub = renorm ? (mn & ~OPS::FMASK) : 0u;
+        // renormalisation: every block for the 22-bit float metrics; every 16 steps for the 6-bit Hamming metrics
+        // (spread <= 12, growth <= 2 per step: 12 + 32 + 2 < 64)
+        if (PACK == 1) {
+            const uint32_t sub = mn & ~OPS::FMASK;
 #pragma unroll
-        for (int s = 0; s < 64; ++s) Kc[s] = ((Kc[s] & met) | OPS::idx(s)) - sub;
+            for (int s = 0; s < 64; ++s) Kc[s] = ((Kc[s] & met) | OPS::idx(s)) - sub;
+        } else {
+#pragma unroll
+            for (int s = 0; s < 64; ++s) Kc[s] = (Kc[s] & met) | OPS::idx(s);
+            if ((tau & 15) == 0) {
+                const uint32_t sub = mn & ~OPS::FMASK;
+#pragma unroll
+                for (int s = 0; s < 64; ++s) Kc[s] -= sub;
+            }
+        }
     };
 
     Raw qd[QD];
 #pragma unroll
-    for (int i = 0; i < QD; ++i) qd[i] = load_block(i);
+    for (int i = 0; i < QD; ++i) qd[i] = load_pair(i);
     uint32_t Bm[4];
+    uint32_t mq0 = 0u, mq1 = 0u;                 // best fields of the first half of the running block
+    static_assert(QD >= 2 && QD % 2 == 0, "the prefetch queue moves by whole blocks");
+    const int npairs = p.T >> 1, nfull = p.T >> 2;
+    // (A loop body of half a block -- smaller code -- was measured: slower, the register shuffling at the extra loop
+    // edge costs more than the instruction fetch it saves.)
+#pragma unroll 1
     for (int blk = 0; blk < nfull; ++blk) {
-        const Raw cur = qd[0];
+        const Raw cur0 = gather(qd[0]), cur1 = gather(qd[1]);
 #pragma unroll
-        for (int i = 0; i + 1 < QD; ++i) qd[i] = qd[i + 1];
-        qd[QD - 1] = load_block(blk + QD);          // software prefetch, QD blocks ahead
-        const int tau0 = 4 * blk;
-        const bool keep_bf = tau0 >= ts_cur;
-        uint32_t *bfp = sm.bf + (tau0 - ts_cur) * BD + tid;
-        uint32_t mn;
-        make_bm(cur, 0, Bm);
-        mn = acs_step<CODE, PACK>(K, Kn, Bm, OPS::INC0 << 0);
-        if (keep_bf) bfp[0 * BD] = mn & OPS::FMASK;
-        make_bm(cur, 1, Bm);
-        mn = acs_step<CODE, PACK>(Kn, K, Bm, OPS::INC0 << 1);
-        if (keep_bf) bfp[1 * BD] = mn & OPS::FMASK;
-        make_bm(cur, 2, Bm);
-        mn = acs_step<CODE, PACK>(K, Kn, Bm, OPS::INC0 << 2);
-        if (keep_bf) bfp[2 * BD] = mn & OPS::FMASK;
-        make_bm(cur, 3, Bm);
-        mn = acs_step<CODE, PACK>(Kn, K, Bm, OPS::INC0 << 3);
-        if (keep_bf) bfp[3 * BD] = mn & OPS::FMASK;
-        const int tau = tau0 + 4;
-        block_end(K, mn, tau);
-        if (tau == p.T) {
-            tb_block<CODE, PACK, true>(sm, ts_cur, tau, nslot, p.D, p.L, p.NJ, outp[0], outp[PACK - 1], valid_mask, p.out_vec8);
-        } else if (tau == next_te) {
-            tb_block<CODE, PACK, false>(sm, ts_cur, tau, nslot, p.D, p.L, p.NJ, outp[0], outp[PACK - 1], valid_mask, p.out_vec8);
+        for (int i = 0; i + 2 < QD; ++i) qd[i] = qd[i + 2];
+        qd[QD - 2] = load_pair(2 * blk + QD);          // software prefetch, QD pairs of steps ahead
+        qd[QD - 1] = load_pair(2 * blk + QD + 1);
+        make_bm(cur0, 0, Bm);
+        mq0 = acs_step<CODE, PACK>(K, Kn, Bm, OPS::INC0 << 0);
+        make_bm(cur0, 1, Bm);
+        mq1 = acs_step<CODE, PACK>(Kn, K, Bm, OPS::INC0 << 1);
+        make_bm(cur1, 0, Bm);
+        const uint32_t m2 = acs_step<CODE, PACK>(K, Kn, Bm, OPS::INC0 << 2);
+        make_bm(cur1, 1, Bm);
+        const uint32_t m3 = acs_step<CODE, PACK>(Kn, K, Bm, OPS::INC0 << 3);
+        const int tau = 4 * blk + 4, tau0 = 4 * blk;
+        if (tau0 >= ts_cur)
+            sm_at<uint4>(sm.bf + (((tau0 - ts_cur) >> 2) * BD + tid) * 16) =
+                make_uint4(mq0 & OPS::FMASK, mq1 & OPS::FMASK, m2 & OPS::FMASK, m3 & OPS::FMASK);
+        block_end(K, m3, tau);
+        if (tau == next_te || tau == p.T) {
+            tb_block<CODE, PACK>(sm, ts_cur, tau, nslot, p.D, p.L, p.NJ, outp[0], outp[PACK - 1], valid_mask, p.out_vec8, tau == p.T);
             ts_cur = tau;
             next_te = tau + p.TBB;
         }
         nslot = (nslot + 1 == p.RB) ? 0 : nslot + 1;
     }
-    if (rem) {
-        // the last 1..3 steps: no block completes, the final traceback starts from best[T]'s field
-        const Raw cur = qd[0];
-        const int tau0 = 4 * nfull;
-        uint32_t *bfp = sm.bf + (tau0 - ts_cur) * BD + tid;
-        const int last = (nslot == 0) ? p.RB - 1 : nslot - 1;
-        uint32_t mn;
+    mq0 = mq1 = 0u;
+    if (npairs & 1) {                            // T mod 4 >= 2: one more pair of steps
+        const Raw cur = gather(qd[0]);
         make_bm(cur, 0, Bm);
-        mn = acs_step<CODE, PACK>(K, Kn, Bm, OPS::INC0 << 0);
-        bfp[0 * BD] = mn & OPS::FMASK;
-        if (rem >= 2) {
-            make_bm(cur, 1, Bm);
-            mn = acs_step<CODE, PACK>(Kn, K, Bm, OPS::INC0 << 1);
-            bfp[1 * BD] = mn & OPS::FMASK;
+        mq0 = acs_step<CODE, PACK>(K, Kn, Bm, OPS::INC0) & OPS::FMASK;
+        make_bm(cur, 1, Bm);
+        mq1 = acs_step<CODE, PACK>(Kn, K, Bm, OPS::INC0 << 1) & OPS::FMASK;
+        qd[0] = qd[1];
+    }
+    if (p.T & 3) {
+        // the last 1..3 steps: no block completes, the final traceback starts from best[T]'s field
+        uint32_t mq2 = 0u;
+        if (p.T & 1) {
+            make_bm(gather(qd[0]), 0, Bm);
+            const uint32_t m = acs_step<CODE, PACK>(K, Kn, Bm, OPS::INC0 << (2 * (npairs & 1))) & OPS::FMASK;
+            if (npairs & 1) mq2 = m; else mq0 = m;
         }
-        if (rem >= 3) {
-            make_bm(cur, 2, Bm);
-            mn = acs_step<CODE, PACK>(K, Kn, Bm, OPS::INC0 << 2);
-            bfp[2 * BD] = mn & OPS::FMASK;
-        }
-        tb_block<CODE, PACK, true>(sm, ts_cur, p.T, last, p.D, p.L, p.NJ, outp[0], outp[PACK - 1], valid_mask, p.out_vec8);
+        const int tau0 = p.T & ~3;
+        sm_at<uint4>(sm.bf + (((tau0 - ts_cur) >> 2) * BD + tid) * 16) = make_uint4(mq0, mq1, mq2, 0u);
+        const int last = (nslot == 0) ? p.RB - 1 : nslot - 1;
+        tb_block<CODE, PACK>(sm, ts_cur, p.T, last, p.D, p.L, p.NJ, outp[0], outp[PACK - 1], valid_mask, p.out_vec8, true);
     }
 }
 
 // hard decision: two u16x2-packed frames per thread
 template <class CODE>
-__global__ void __launch_bounds__(BD) viterbi_fast_kernel_hard(const Params p) { viterbi_fast_body<CODE, 2, 2>(p); }
+__global__ void __launch_bounds__(BD) viterbi_fast_kernel_hard(const Params p) { viterbi_fast_body<CODE, 2, CPB_QD_HARD>(p); }
 // soft / unquantized: one frame per thread, 32-bit keys
 template <class CODE>
-__global__ void __launch_bounds__(BD, 12) viterbi_fast_kernel_soft(const Params p) { viterbi_fast_body<CODE, 1, 1>(p); }
+__global__ void __launch_bounds__(BD, 12) viterbi_fast_kernel_soft(const Params p) { viterbi_fast_body<CODE, 1, 2>(p); }
 
 // Per-frame power-of-two scale for float input: the largest |value| of the frame (after the +-500 clip in 'soft'
 // mode, convcode.py:718-719; including the -1 padding of 'unquantized', :729-732) maps to at most 2^QBITS.
@@ -981,7 +1036,7 @@ int cpb_viterbi_decode(const cpbTrellis *t, const void *coded_dev, int in_dtype,
         if (rc) return rc;
         if (fast::smem_bytes(p.RB, p.TBB, pack) > dp.smem_optin) { ws.release(); return CPB_EUNSUPPORTED; }
         p.met_mask = (pack == 2) ? ~fast::KeyOps<2>::FMASK : ~fast::KeyOps<1>::FMASK;
-        if (pack == 2) p.in_aligned = ((n_in % 8) == 0 && (((uintptr_t)coded_dev) % 8) == 0) ? 1 : 0;
+        if (pack == 2) p.in_aligned = ((n_in % 4) == 0 && (((uintptr_t)coded_dev) % 4) == 0) ? 1 : 0;
         else p.in_aligned = ((n_in % 4) == 0 && (((uintptr_t)coded_dev) % 16) == 0) ? 1 : 0;
         if (pack == 1) {
             float *sc = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(ws.ptr) + 256);

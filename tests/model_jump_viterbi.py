@@ -71,7 +71,7 @@ def acs_forward(coded, G0, G1, mode="hard", M=6, key_bits=16, qbits=None):
             fld = (Kn >> B) & 63
             assert np.array_equal(fld, np.arange(S))
             Kn = ((Kn >> FB) << FB) | np.arange(S)
-            if tau % 8 == 0:
+            if tau % 16 == 0:
                 Kn -= (mn >> FB) << FB
         K = Kn
     return bf, nib, T, L
