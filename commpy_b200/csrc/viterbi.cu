@@ -196,7 +196,7 @@ static size_t smem_bytes(int RB, int TBB, int pack)
     size_t b = (size_t)RB * 8 * pack * BD * sizeof(uint32_t);
     b += (size_t)TBB * BD * sizeof(uint32_t);
     b += 16 * sizeof(uint4);
-    b += (size_t)2 * TASK_CAP * sizeof(uint32_t);
+    b += (size_t)2 * (TASK_CAP + BD) * sizeof(uint32_t);       // + one scratch slot per lane
     b += (size_t)BD * pack * sizeof(uint32_t);
     return b;
 }
@@ -294,7 +294,6 @@ __device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int t
     int bslot0 = slot_last;
     if (jte == 3) bslot0 = (slot_last == 0) ? sm.RB - 1 : slot_last - 1;
     uint32_t acc[PACK];
-    int hi[PACK];
     Jumper<PACK, uint32_t> jw[PACK];
     int ntask = 0;                                      // warp-uniform
     // best fields of the block that holds te
@@ -303,19 +302,20 @@ __device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int t
     const uint32_t bwe = (jte == 0) ? bq.x : (jte == 1) ? bq.y : (jte == 2) ? bq.z : bq.w;
 #pragma unroll
     for (int fi = 0; fi < PACK; ++fi) {
-        hi[fi] = te;
         jw[fi].init(sm, bslot0, lane, fi, (bwe >> (16 * fi)) & 0x3FFu);
         sm_at<uint32_t>(sm.outbits + (lane + BD * fi) * 4) = 0u;
     }
     // one window: does the current path of frame fi pass through best[tau]?  (j = sub-step of tau, bw = best fields)
-    // Branch free: the task slot comes from a ballot, the store and the path switch are predicated.
+    // Branch free, and the only serial dependency from one window to the next is xor-and -> compare -> select on the
+    // path register: the task slot comes from a ballot, the task is stored unconditionally (lanes that do not retire
+    // write a scratch slot of their own).
+    uint32_t hi_sh[PACK];                               // (hi - ts) << 17, the form the task word wants
+#pragma unroll
+    for (int fi = 0; fi < PACK; ++fi) hi_sh[fi] = (uint32_t)(te - ts) << 17;
+    const int scratch = sm.tasks + (TASK_CAP + lane) * 8;
     auto check = [&](int tau, int j, uint32_t bw) {
         const uint32_t msk = 63u << (j + 1);
         const uint32_t twc = (uint32_t)lane | ((uint32_t)(tau - ts) << 12) | ((uint32_t)((tau - 1 - j - ts) >> 2) << 22);
-        if (__builtin_expect(ntask > TASK_CAP - 2 * BD, 0)) {    // (warp-uniform, rare) queue nearly full: drain it
-            tb_run_tasks<PACK>(sm, ntask, ts, NJ, shc);
-            ntask = 0;
-        }
 #pragma unroll
         for (int fi = 0; fi < PACK; ++fi) {
             const uint32_t b = (bw >> (16 * fi)) & 0x3FFu;
@@ -323,13 +323,19 @@ __device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int t
             const uint32_t vote = __ballot_sync(0xffffffffu, miss);
             const int qi = ntask + __popc(vote & lt_mask);
             ntask += __popc(vote);
-            if (miss)                                            // retire the path: it served the windows (tau, hi]
-                sm_at<uint2>(sm.tasks + qi * 8) = make_uint2(
-                    twc | ((uint32_t)fi << 5) | (((uint32_t)jw[fi].rowoff / (uint32_t)Jumper<PACK, uint32_t>::ROWB) << 6) |
-                        ((uint32_t)(hi[fi] - ts) << 17),
-                    jw[fi].reg);
-            hi[fi] = miss ? tau : hi[fi];
+            // retire the path (it served the windows (tau, hi]) and start the one of best[tau]
+            sm_at<uint2>(miss ? sm.tasks + qi * 8 : scratch) = make_uint2(
+                twc | ((uint32_t)fi << 5) | (((uint32_t)jw[fi].rowoff / (uint32_t)Jumper<PACK, uint32_t>::ROWB) << 6) | hi_sh[fi],
+                jw[fi].reg);
+            hi_sh[fi] = miss ? ((uint32_t)(tau - ts) << 17) : hi_sh[fi];
             jw[fi].reg = miss ? b : jw[fi].reg;
+        }
+    };
+    // a block of 4 windows can queue up to 8 * 32 tasks: drain the queue first when that might not fit (rare)
+    auto make_room = [&]() {
+        if (__builtin_expect(ntask > TASK_CAP - 8 * BD, 0)) {
+            tb_run_tasks<PACK>(sm, ntask, ts, NJ, shc);
+            ntask = 0;
         }
     };
     // ---- phase A: the rest of the block that holds te, then whole blocks down to ts
@@ -337,6 +343,7 @@ __device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int t
     for (int j = jte - 1; j >= 0; --j, --tau)
         check(tau, j, (j == 0) ? bq.x : (j == 1) ? bq.y : bq.z);
     while (tau > ts) {
+        make_room();
 #pragma unroll
         for (int fi = 0; fi < PACK; ++fi) jw[fi].jump();
         bfo -= BD * 16;
@@ -354,7 +361,7 @@ __device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int t
         for (int fi = 0; fi < PACK; ++fi) jw[fi].jump();
     }
 #pragma unroll
-    for (int fi = 0; fi < PACK; ++fi) acc[fi] = tb_contribution(jw[fi].reg, 0, ts, hi[fi], ts, shc);
+    for (int fi = 0; fi < PACK; ++fi) acc[fi] = tb_contribution(jw[fi].reg, 0, ts, ts + (int)(hi_sh[fi] >> 17), ts, shc);
     // ---- phase B: the retired paths
     tb_run_tasks<PACK>(sm, ntask, ts, NJ, shc);
 #pragma unroll
@@ -438,7 +445,7 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
         sm.nib = q; q += p.RB * NW * BD * (int)sizeof(uint32_t);
         sm.bf = q; q += p.TBB * BD * (int)sizeof(uint32_t);
         sm.lut = q; q += 16 * (int)sizeof(uint4);
-        sm.tasks = q; q += 2 * TASK_CAP * (int)sizeof(uint32_t);
+        sm.tasks = q; q += 2 * (TASK_CAP + BD) * (int)sizeof(uint32_t);
         sm.outbits = q;
     }
     if (PACK == 2) {
