@@ -14,12 +14,13 @@ CPB_OK, CPB_EINVAL, CPB_EUNSUPPORTED, CPB_ECUDA, CPB_ENOMEM, CPB_ETRELLIS = rang
 CPB_U8, CPB_F32 = 0, 1
 VITERBI_MODES = {"hard": 0, "soft": 1, "unquantized": 2}
 LDPC_FP32, LDPC_FP64 = 0, 1
+OPT_VITERBI_FORCE_GENERIC, OPT_LDPC_NO_BULK = 0, 1
 
 # every symbol include/commpy_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "cpb_strerror", "cpb_last_cuda_error", "cpb_version", "cpb_device_info",
+    "cpb_strerror", "cpb_last_cuda_error", "cpb_version", "cpb_device_info", "cpb_set_option", "cpb_get_option",
     "cpb_trellis_create", "cpb_trellis_destroy", "cpb_trellis_fast_path",
-    "cpb_viterbi_sizes", "cpb_viterbi_workspace_bytes", "cpb_viterbi_decode", "cpb_viterbi_decode_host",
+    "cpb_viterbi_sizes", "cpb_viterbi_workspace_bytes", "cpb_viterbi_decode", "cpb_viterbi_decode_host", "cpb_viterbi_decode_packed", "cpb_viterbi_decode_host_packed",
     "cpb_map_decode", "cpb_turbo_decode",
     "cpb_ldpc_create", "cpb_ldpc_destroy", "cpb_ldpc_workspace_bytes", "cpb_ldpc_minsum", "cpb_ldpc_sumproduct",
     "cpb_modem_create", "cpb_modem_destroy", "cpb_modem_is_separable", "cpb_demod_soft", "cpb_demod_hard",
@@ -64,6 +65,11 @@ def check(status, what=""):
     if status == CPB_EUNSUPPORTED:
         raise NotImplementedError(msg)
     raise CommpyB200Error(msg + " | " + lib.cpb_last_cuda_error().decode())
+
+
+def set_option(option_id, value):
+    """cpb_set_option: explicit test / cross-check switches (the library never reads the environment)."""
+    check(load().cpb_set_option(int(option_id), int(value)), "set_option")
 
 
 def require_cuda():

@@ -1,9 +1,20 @@
 // Status strings, device properties, scratch allocation (host-side plumbing of libcommpy_b200.so).
+#include <atomic>
+
 #include "common.cuh"
 
 namespace cpb {
 
 thread_local char g_cuda_err[256] = "";
+
+static std::atomic<int> g_options[CPB_OPT_COUNT];
+int option(int id) { return (id >= 0 && id < CPB_OPT_COUNT) ? g_options[id].load(std::memory_order_relaxed) : 0; }
+int set_option(int id, int v)
+{
+    if (id < 0 || id >= CPB_OPT_COUNT) return CPB_EINVAL;
+    g_options[id].store(v, std::memory_order_relaxed);
+    return CPB_OK;
+}
 
 int record_cuda_error(cudaError_t e, const char *what, const char *file, int line)
 {
@@ -79,7 +90,15 @@ const char *cpb_strerror(int status)
 
 const char *cpb_last_cuda_error(void) { return cpb::g_cuda_err; }
 
-int cpb_version(void) { return 100; }
+int cpb_version(void) { return 200; }
+
+int cpb_set_option(int option_id, int value) { return cpb::set_option(option_id, value); }
+int cpb_get_option(int option_id, int *value)
+{
+    if (!value || option_id < 0 || option_id >= CPB_OPT_COUNT) return CPB_EINVAL;
+    *value = cpb::option(option_id);
+    return CPB_OK;
+}
 
 int cpb_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *global_mem_bytes)
 {

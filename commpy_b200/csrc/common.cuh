@@ -38,6 +38,9 @@ struct Scratch {
     void release();
 };
 
+// explicit test / experiment switches (cpb_set_option); read with relaxed atomics, never from the environment
+int option(int id);
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 }  // namespace cpb

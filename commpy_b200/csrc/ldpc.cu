@@ -630,7 +630,7 @@ static int run(const cpbLdpc *h, T *llr, int64_t batch, int n_iters, int spa, ui
         const unsigned vn_blocks = (unsigned)ceil_div((int64_t)h->n * G, 256);
         // bulk-copy staged check pass: min-sum, row degree <= 32, frame chunks of 256 or 128
         // (CPB_LDPC_NO_BULK=1 forces the register-staged kernels: used by the test that compares the two paths)
-        bool use_bulk = !spa && h->max_row_deg <= bulk::MAXDEG && !getenv("CPB_LDPC_NO_BULK");
+        bool use_bulk = !spa && h->max_row_deg <= bulk::MAXDEG && !option(CPB_OPT_LDPC_NO_BULK);
         int FT = (F % 256 == 0) ? 256 : ((F % 128 == 0) ? 128 : 0);
         int nchunks = 0, bulk_grid = 0;
         size_t bulk_smem = 0;

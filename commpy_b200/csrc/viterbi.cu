@@ -25,17 +25,10 @@
 #include <vector>
 
 #include "common.cuh"
+#include "handles.cuh"
 
 using namespace cpb;
 
-struct cpbTrellis {
-    int k, n, M, S, I;
-    std::vector<int32_t> next_state, output;   // host copies, S x I
-    int32_t *pred_dev = nullptr;               // S*I entries: prev_state | input<<8 | output<<16, (p asc, u asc)
-    int32_t *next_dev = nullptr, *out_dev = nullptr;   // S x I tables on the device (BCJR)
-    int fast_id = 0;
-    int device = 0;
-};
 
 // ------------------------------------------------------------------------------------------------
 // compile-time description of a rate-1/2 feed-forward code in CommPy's Trellis convention
@@ -120,7 +113,7 @@ struct Params {
     int mode;                    // CPB_VITERBI_*
     const float *frame_scale;    // float input: power-of-two scale per frame (device)
     uint8_t *out;
-    int out_vec8;                // 1: rows of out are 8-byte aligned
+    int out_vec8;                // 1: rows of out are 8-byte aligned; 2: out is bit-packed (np.packbits order), L/8 bytes per row
     int in_aligned;              // 1: rows of coded are 4-byte (u8) / 16-byte (f32) aligned
     uint32_t met_mask;           // metric bits of a key, passed at run time so the key refresh stays one LOP3
 };
@@ -370,6 +363,23 @@ __device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int t
         if (!((valid_mask >> fi) & 1)) continue;
         uint8_t *orow = (fi == 0 ? out0 : out1);
         const int nbw = te - ts;
+        if (out_vec8 == 2) {
+            // bit-packed output (host launcher guarantees p0 % 8 == 0, TBB % 8 == 0, L % 8 == 0): bit p of the frame is
+            // bit 7 - (p & 7) of byte p >> 3
+            unsigned long long a64 = a32;
+            int nb = nbw;
+            if (final) {
+                Jumper<PACK, unsigned long long> t;
+                t.init(sm, bslot0, lane, fi, (unsigned long long)((bwe >> (16 * fi)) & 0x3FFu));
+#pragma unroll 1
+                for (int i = 0; i < NJ; ++i) t.jump();
+                a64 |= (t.reg >> (jte + 1 + shc)) << nbw;          // bits T-D+2 .. L-1 follow the last window
+                nb = L - p0;
+            }
+            for (int g8 = 0; g8 < nb; g8 += 8)
+                orow[(p0 + g8) >> 3] = (uint8_t)(__brev((uint32_t)(a64 >> g8) & 0xffu) >> 24);
+            continue;
+        }
         if (out_vec8 && p0 >= 0 && (p0 & 7) == 0 && (nbw & 7) == 0) {
             // 8 decoded bits -> 8 bytes per store
             for (int g8 = 0; g8 < nbw; g8 += 8) {
@@ -430,7 +440,7 @@ __device__ __forceinline__ void tb_block(const Smem<PACK> sm, int ts, int te, in
         tb_block_call<CODE, PACK>(sm, ts, te, slot_last, D, L, NJ, out0, out1, valid_mask, out_vec8, final);
 }
 
-template <class CODE, int PACK, int QD>
+template <class CODE, int PACK, int QD, int IOP>
 __device__ __forceinline__ void viterbi_fast_body(const Params &p)
 {
     using OPS = KeyOps<PACK>;
@@ -452,7 +462,9 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
         // hard-decision branch metrics of two frames: entry idx = r0A | r1A<<1 | r0B<<2 | r1B<<3,
         // component o = Hamming distance to output symbol o (convcode.py:579) in the metric field, frame B in the high half
         if (tid < 16) {
-            const int a = ((tid & 1) << 1) | ((tid >> 1) & 1), b = (((tid >> 2) & 1) << 1) | ((tid >> 3) & 1);
+            // table index: r0A | r1A<<1 | r0B<<2 | r1B<<3 (byte input) or symA | symB<<2 with sym = r0<<1 | r1 (packed input)
+            const int a = IOP ? (tid & 3) : (((tid & 1) << 1) | ((tid >> 1) & 1));
+            const int b = IOP ? (tid >> 2) : ((((tid >> 2) & 1) << 1) | ((tid >> 3) & 1));
             uint32_t e[4];
             for (int o = 0; o < 4; ++o) e[o] = ((uint32_t)__popc(o ^ a) << FB) | ((uint32_t)__popc(o ^ b) << (16 + FB));
             sm_at<uint4>(sm.lut + tid * 16) = make_uint4(e[0], e[1], e[2], e[3]);
@@ -469,7 +481,7 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
     for (int fi = 0; fi < PACK; ++fi) {
         fr[fi] = base + (int64_t)fi * BD + tid;
         if (fr[fi] < p.batch) valid_mask |= 1 << fi; else fr[fi] = p.batch - 1;
-        outp[fi] = p.out + fr[fi] * (int64_t)p.L;
+        outp[fi] = p.out + fr[fi] * (int64_t)(IOP ? (p.L >> 3) : p.L);
     }
 
     // float input: the frame's own power-of-two scale (frame_scale_kernel), so a frame decodes identically
@@ -505,7 +517,13 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
         if (PACK == 2) {
             // a = the 4 coded bytes of frame A, b = frame B; past the data: zeros (convcode.py:727-728)
             uint32_t a = 0u, b = 0u;
-            if (p.in_aligned && pr < npairs_in) {
+            if (IOP) {
+                // bit-packed input: the byte that holds the pair (2 pairs of steps per byte, first element in bit 7)
+                if (pr < npairs_in) {
+                    a = __ldg(c8 + fr[0] * (p.n_in >> 3) + (pr >> 1));
+                    b = __ldg(c8 + fr[PACK - 1] * (p.n_in >> 3) + (pr >> 1));
+                }
+            } else if (p.in_aligned && pr < npairs_in) {
                 a = __ldg(reinterpret_cast<const uint32_t *>(c8 + fr[0] * p.n_in) + pr);
                 b = __ldg(reinterpret_cast<const uint32_t *>(c8 + fr[PACK - 1] * p.n_in) + pr);
             } else {
@@ -547,12 +565,19 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
     // Byte (w >> 24) = table index of step a | table index of step b << 4.
     auto gather = [&](const Raw &r) {
         Raw g = r;
-        if (PACK == 2) g.w[0] = (r.w[0] & 0x01010101u) * 0x01021020u + (r.w[1] & 0x01010101u) * 0x04084080u;
+        if (PACK == 2 && !IOP) g.w[0] = (r.w[0] & 0x01010101u) * 0x01021020u + (r.w[1] & 0x01010101u) * 0x04084080u;
         return g;
     };
     // the four branch metrics (in the metric field) of step h (0 / 1) of a (gathered) pair
-    auto make_bm = [&](const Raw &r, int h, uint32_t (&Bm)[4]) {
-        if (PACK == 2) {
+    // (bit-packed input: `odd` says whether the pair is the second one of its byte)
+    auto make_bm = [&](const Raw &r, int h, uint32_t (&Bm)[4], int odd = 0) {
+        if (PACK == 2 && IOP) {
+            // received symbol of frame A = bits (7,6) >> 2*(2*odd + h) of its byte, same for frame B; table index = A | B << 2
+            const int sh = 2 * (2 * odd + h);
+            const uint32_t off = (((r.w[0] << sh) >> 2) & 0x30u) | ((r.w[1] << sh) & 0xC0u);
+            const uint4 e = sm_at<uint4>(sm.lut + (int)off);
+            Bm[0] = e.x; Bm[1] = e.y; Bm[2] = e.z; Bm[3] = e.w;
+        } else if (PACK == 2) {
             const uint32_t off = (r.w[0] >> (h ? 24 : 20)) & 0xF0u;      // 16 * table index
             const uint4 e = sm_at<uint4>(sm.lut + (int)off);
             Bm[0] = e.x; Bm[1] = e.y; Bm[2] = e.z; Bm[3] = e.w;
@@ -644,9 +669,9 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
         mq0 = acs_step<CODE, PACK>(K, Kn, Bm, OPS::INC0 << 0);
         make_bm(cur0, 1, Bm);
         mq1 = acs_step<CODE, PACK>(Kn, K, Bm, OPS::INC0 << 1);
-        make_bm(cur1, 0, Bm);
+        make_bm(cur1, 0, Bm, 1);
         const uint32_t m2 = acs_step<CODE, PACK>(K, Kn, Bm, OPS::INC0 << 2);
-        make_bm(cur1, 1, Bm);
+        make_bm(cur1, 1, Bm, 1);
         const uint32_t m3 = acs_step<CODE, PACK>(Kn, K, Bm, OPS::INC0 << 3);
         const int tau = 4 * blk + 4, tau0 = 4 * blk;
         if (tau0 >= ts_cur)
@@ -673,7 +698,7 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
         // the last 1..3 steps: no block completes, the final traceback starts from best[T]'s field
         uint32_t mq2 = 0u;
         if (p.T & 1) {
-            make_bm(gather(qd[0]), 0, Bm);
+            make_bm(gather(qd[0]), 0, Bm, npairs & 1);
             const uint32_t m = acs_step<CODE, PACK>(K, Kn, Bm, OPS::INC0 << (2 * (npairs & 1))) & OPS::FMASK;
             if (npairs & 1) mq2 = m; else mq0 = m;
         }
@@ -686,10 +711,13 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
 
 // hard decision: two u16x2-packed frames per thread
 template <class CODE>
-__global__ void __launch_bounds__(BD) viterbi_fast_kernel_hard(const Params p) { viterbi_fast_body<CODE, 2, CPB_QD_HARD>(p); }
+__global__ void __launch_bounds__(BD) viterbi_fast_kernel_hard(const Params p) { viterbi_fast_body<CODE, 2, CPB_QD_HARD, 0>(p); }
+// the same with bit-packed input and output (1 bit per coded / decoded bit, np.packbits order): 8x less HBM and PCIe traffic
+template <class CODE>
+__global__ void __launch_bounds__(BD) viterbi_fast_kernel_hard_packed(const Params p) { viterbi_fast_body<CODE, 2, CPB_QD_HARD, 1>(p); }
 // soft / unquantized: one frame per thread, 32-bit keys
 template <class CODE>
-__global__ void __launch_bounds__(BD, 12) viterbi_fast_kernel_soft(const Params p) { viterbi_fast_body<CODE, 1, 2>(p); }
+__global__ void __launch_bounds__(BD, 12) viterbi_fast_kernel_soft(const Params p) { viterbi_fast_body<CODE, 1, 2, 0>(p); }
 
 // Per-frame power-of-two scale for float input: the largest |value| of the frame (after the +-500 clip in 'soft'
 // mode, convcode.py:718-719; including the -1 padding of 'unquantized', :729-732) maps to at most 2^QBITS.
@@ -725,11 +753,12 @@ __global__ void frame_scale_kernel(const float *__restrict__ x, int64_t n_in, in
     }
 }
 
-template <class CODE, int PACK>
+template <class CODE, int PACK, int IOP = 0>
 static int launch(const Params &p, cudaStream_t st)
 {
     const size_t smem = smem_bytes(p.RB, p.TBB, PACK);
-    void (*kern)(const Params) = (PACK == 2) ? viterbi_fast_kernel_hard<CODE> : viterbi_fast_kernel_soft<CODE>;
+    void (*kern)(const Params) = IOP ? viterbi_fast_kernel_hard_packed<CODE>
+                                     : (PACK == 2) ? viterbi_fast_kernel_hard<CODE> : viterbi_fast_kernel_soft<CODE>;
     static thread_local size_t attr_set[64] = {0};       // per device: largest dynamic smem size already opted in
     int dev = 0;
     cudaGetDevice(&dev);
@@ -963,10 +992,9 @@ static int resolve_depth(const cpbTrellis *t, int64_t L, int tb_depth)
 static bool use_fast(const cpbTrellis *t, int D, int mode, int in_dtype)
 {
     if (t->fast_id == 0) return false;
-    // test hook: CPB_VITERBI_FORCE_GENERIC=1 routes every trellis through the table-driven kernel, so the two
+    // cpb_set_option(CPB_OPT_VITERBI_FORCE_GENERIC, 1) routes every trellis through the table-driven kernel, so the two
     // independent implementations can be compared against each other at full size (tests/test_viterbi_gpu.py)
-    const char *force = getenv("CPB_VITERBI_FORCE_GENERIC");
-    if (force && force[0] == '1') return false;
+    if (option(CPB_OPT_VITERBI_FORCE_GENERIC)) return false;
     if (D < t->M + 1 || D > fast::DMAX) return false;
     if (mode == CPB_VITERBI_HARD) return in_dtype == CPB_U8;
     return in_dtype == CPB_F32;
@@ -983,6 +1011,26 @@ static size_t generic_chunk(const cpbTrellis *t, int64_t batch, int64_t T, int64
     if (chunk > need) chunk = need;
     *stride = chunk;
     return (size_t)((T + 1) * (int64_t)(t->S + 1) * chunk);
+}
+
+static int launch_fast(const cpbTrellis *t, const fast::Params &p, int pack, int packed_io, cudaStream_t st)
+{
+    if (packed_io) {
+        if (t->fast_id == 1) return fast::launch<Code133_171, 2, 1>(p, st);
+        if (t->fast_id == 2) return fast::launch<Code171_133, 2, 1>(p, st);
+        if (t->fast_id == 3) return fast::launch<Code5_43, 2, 1>(p, st);
+        return fast::launch<Code5_7, 2, 1>(p, st);
+    }
+    if (pack == 2) {
+        if (t->fast_id == 1) return fast::launch<Code133_171, 2>(p, st);
+        if (t->fast_id == 2) return fast::launch<Code171_133, 2>(p, st);
+        if (t->fast_id == 3) return fast::launch<Code5_43, 2>(p, st);
+        return fast::launch<Code5_7, 2>(p, st);
+    }
+    if (t->fast_id == 1) return fast::launch<Code133_171, 1>(p, st);
+    if (t->fast_id == 2) return fast::launch<Code171_133, 1>(p, st);
+    if (t->fast_id == 3) return fast::launch<Code5_43, 1>(p, st);
+    return fast::launch<Code5_7, 1>(p, st);
 }
 
 extern "C" {
@@ -1054,17 +1102,7 @@ int cpb_viterbi_decode(const cpbTrellis *t, const void *coded_dev, int in_dtype,
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) { ws.release(); return record_cuda_error(e, "frame_scale_kernel", __FILE__, __LINE__); }
         }
-        if (pack == 2) {
-            if (t->fast_id == 1) rc = fast::launch<Code133_171, 2>(p, st);
-            else if (t->fast_id == 2) rc = fast::launch<Code171_133, 2>(p, st);
-            else if (t->fast_id == 3) rc = fast::launch<Code5_43, 2>(p, st);
-            else rc = fast::launch<Code5_7, 2>(p, st);
-        } else {
-            if (t->fast_id == 1) rc = fast::launch<Code133_171, 1>(p, st);
-            else if (t->fast_id == 2) rc = fast::launch<Code171_133, 1>(p, st);
-            else if (t->fast_id == 3) rc = fast::launch<Code5_43, 1>(p, st);
-            else rc = fast::launch<Code5_7, 1>(p, st);
-        }
+        rc = launch_fast(t, p, pack, 0, st);
         ws.release();
         return rc;
     }
@@ -1095,6 +1133,35 @@ int cpb_viterbi_decode(const cpbTrellis *t, const void *coded_dev, int in_dtype,
     }
     ws.release();
     return CPB_OK;
+}
+
+
+int cpb_viterbi_decode_packed(const cpbTrellis *t, const uint8_t *coded_packed_dev, int64_t batch, int64_t n_in,
+                              int tb_depth, uint8_t *out_packed_dev, void *stream)
+{
+    if (t && batch == 0) return CPB_OK;
+    if (!t || !coded_packed_dev || !out_packed_dev || batch < 0 || n_in <= 0) return CPB_EINVAL;
+    int64_t L, T;
+    cpb_viterbi_sizes(t, n_in, &L, &T);
+    const int D = resolve_depth(t, L, tb_depth);
+    if (L <= 0 || D < 2 || T < D - 1 || T > (1 << 24)) return CPB_EINVAL;
+    // whole bytes per row, whole output bytes per traceback block
+    if (!use_fast(t, D, CPB_VITERBI_HARD, CPB_U8) || (n_in % 8) != 0 || (L % 8) != 0 || ((D - 2) % 4) != 0 ||
+        (CPB_VITERBI_TBB % 8) != 0)
+        return CPB_EUNSUPPORTED;
+    const DeviceProps &dp = device_props();
+    fast::Params p{};
+    p.coded = coded_packed_dev; p.n_in = n_in; p.batch = batch;
+    p.L = (int)L; p.T = (int)T; p.D = D;
+    p.TBB = CPB_VITERBI_TBB;
+    p.NJ = (D > 8) ? (D - 8 + fast::B - 1) / fast::B : 0;
+    p.RB = p.NJ + p.TBB / fast::B;
+    p.mode = CPB_VITERBI_HARD; p.out = out_packed_dev;
+    p.out_vec8 = 2;
+    p.in_aligned = 0;
+    p.met_mask = ~fast::KeyOps<2>::FMASK;
+    if (fast::smem_bytes(p.RB, p.TBB, 2) > dp.smem_optin) return CPB_EUNSUPPORTED;
+    return launch_fast(t, p, 2, 1, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -283,17 +283,30 @@ class ConvLinkGPU:
         _lib.check(rc, "count_errors")
         return dec
 
-    def link_performance(self, SNRs, send_max, err_min):
+    def link_performance(self, SNRs, send_max, err_min, return_counters=False, stop_early=True):
         """BER per SNR (dB, `SNR = Eb/N0 + 10 log10(bits/symbol)` as in the reference's examples,
         conv_encode_decode.py:102; the code rate enters through `set_SNR_dB`, channels.py:74).  A point ends
         when the GLOBAL counters reach `err_min` errors or `send_max` bits; like the reference the sweep stops after
         the first point that ends below `err_min` errors (links.py:339-341).  The stop rule is evaluated once per
-        batch (frames_per_batch * world_size frames), not once per frame."""
+        batch (frames_per_batch * world_size frames), not once per frame.
+
+        Nothing on the critical path waits for the host: the bit count of a point is known in advance, and the error
+        count of batch b is read (from a pinned snapshot) while batch b+1 is already running -- a batch issued after the
+        error threshold was crossed is discarded, so the counters are exactly those of the in-order rule.
+        With return_counters=True also returns the summed [bit errors, frame errors, bits] tensor of all points.
+        stop_early=False measures every point of the sweep (the reference abandons the sweep after the first point that
+        ends below err_min errors)."""
         torch = _lib.require_cuda()
         BERs = np.zeros(len(SNRs))
         batch_index = 0
+        _, world, _ = parallel.world()
+        bits_per_batch = self.frames * max(world, 1) * self.frame_bits
+        grand = torch.zeros(3, dtype=torch.int64, device="cuda")
         for i, snr in enumerate(SNRs):
             tot = torch.zeros(3, dtype=torch.int64, device="cuda")          # bit errors, frame errors, bits sent
+            hist = []                                                        # (device snapshot, pinned copy, event)
+            bits_known = 0
+            chosen = None
             while True:
                 msg, y, nv = self.make_batch(float(snr), batch_index, torch)
                 batch_index += 1
@@ -301,11 +314,27 @@ class ConvLinkGPU:
                 self.receive_decode_count(msg, y, nv, local, torch)
                 local[2] = msg.numel()
                 parallel.allreduce_counters(local)
-                tot += local
-                c = tot.cpu().numpy()
-                if not parallel.stop_rule(c, send_max, err_min):
+                tot = tot + local
+                host = torch.empty(3, dtype=torch.int64).pin_memory()
+                host.copy_(tot, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                hist.append((tot, host, ev))
+                bits_known += bits_per_batch
+                if len(hist) >= 2:                                           # batch b-1, while batch b runs
+                    hist[-2][2].synchronize()
+                    if int(hist[-2][1][0]) >= err_min:
+                        chosen = hist[-2]
+                        break
+                if bits_known >= send_max:
+                    hist[-1][2].synchronize()
+                    chosen = hist[-1]
                     break
+            c = chosen[1].numpy()
+            grand += chosen[0]
             BERs[i] = c[0] / c[2]
-            if c[0] < err_min:
+            if stop_early and c[0] < err_min:
                 break
+        if return_counters:
+            return BERs, grand
         return BERs

@@ -11,7 +11,8 @@
  *    cpb_strerror() maps a status to text, cpb_last_cuda_error() returns the failing CUDA call's text.
  *  - "_dev" pointers are device memory on the CURRENT CUDA device, caller-owned (torch tensors or cudaMalloc);
  *    "_host" pointers are host memory (pageable or pinned).  The library allocates only the opaque
- *    handles created here and, when workspace == NULL, stream-ordered scratch (cudaMallocAsync).
+ *    handles created here (a handle also owns the streams / staging buffers of the *_host calls made with it)
+ *    and, when workspace == NULL, stream-ordered scratch (cudaMallocAsync).  No global mutable state.
  *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device-buffer entry
  *    points are stream-ordered and never synchronise; *_host entry points return after their output
  *    host buffer is complete.
@@ -40,6 +41,13 @@ const char *cpb_strerror(int status);
 const char *cpb_last_cuda_error(void);
 int cpb_version(void);                     /* 10000*major + 100*minor + patch */
 int cpb_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *global_mem_bytes);
+/* Explicit switches for tests and kernel cross-checks (process wide, default 0).  The library never reads the
+ * environment.  They select between kernels that implement the SAME reference semantics. */
+#define CPB_OPT_VITERBI_FORCE_GENERIC 0   /* 1: every trellis goes through the table-driven Viterbi kernel */
+#define CPB_OPT_LDPC_NO_BULK 1            /* 1: min-sum check pass without the bulk-copy staged kernel    */
+#define CPB_OPT_COUNT 8
+int cpb_set_option(int option_id, int value);
+int cpb_get_option(int option_id, int *value);
 
 /* element types of decoder inputs */
 #define CPB_U8 0
@@ -75,6 +83,17 @@ int cpb_viterbi_decode(const cpbTrellis *t, const void *coded_dev, int in_dtype,
 /* Host-buffer form (what a CommPy caller has): chunked H2D -> decode -> D2H pipeline on internal streams. */
 int cpb_viterbi_decode_host(const cpbTrellis *t, const void *coded_host, int in_dtype, int64_t batch,
                             int64_t n_in, int tb_depth, int mode, uint8_t *out_bits_host);
+/*
+ * Bit-packed hard decision: 1 bit per coded bit in, 1 bit per decoded bit out, both in numpy.packbits order (element e
+ * of a row is bit 7 - (e & 7) of byte e >> 3).  coded_packed: batch x n_in/8 bytes, out_packed: batch x L/8 bytes.
+ * Same decision rule as cpb_viterbi_decode(CPB_VITERBI_HARD): 8x less HBM and PCIe traffic for the same answer.
+ * CPB_EUNSUPPORTED unless the trellis has a register-resident fast path, n_in % 16 == 0 and (tb_depth - 2) % 4 == 0
+ * (the default depth 30 of a K = 7 code qualifies).
+ */
+int cpb_viterbi_decode_packed(const cpbTrellis *t, const uint8_t *coded_packed_dev, int64_t batch, int64_t n_in,
+                              int tb_depth, uint8_t *out_packed_dev, void *stream);
+int cpb_viterbi_decode_host_packed(const cpbTrellis *t, const uint8_t *coded_packed_host, int64_t batch,
+                                   int64_t n_in, int tb_depth, uint8_t *out_packed_host);
 
 /* ---- BCJR / turbo: commpy/channelcoding/turbo.py:163-251 map_decode, :254-333 turbo_decode ------ */
 /*

@@ -168,14 +168,18 @@ def test_ldpc_bulk_copy_check_pass_exact(batch, monkeypatch):
     want_dec = want_dec.reshape(n, batch).T
     want_out = want_out.reshape(n, batch).T
     assert (want_it < 20).sum() > batch // 4 and (want_it == 20).sum() >= 1
-    monkeypatch.delenv("CPB_LDPC_NO_BULK", raising=False)
+    from commpy_b200 import _lib
+    _lib.set_option(_lib.OPT_LDPC_NO_BULK, 0)
     dec64, out64, it64 = ldpc_bp_decode_batch(llr.copy(), params, 20, "fp64", return_iters=True)
     assert np.array_equal(dec64.cpu().numpy(), want_dec)
     assert np.array_equal(out64.cpu().numpy(), want_out)
     assert np.array_equal(it64.cpu().numpy(), want_it)
     dec32, out32, it32 = ldpc_bp_decode_batch(llr.astype(np.float32), params, 20, "fp32", return_iters=True)
-    monkeypatch.setenv("CPB_LDPC_NO_BULK", "1")
-    dec32r, out32r, it32r = ldpc_bp_decode_batch(llr.astype(np.float32), params, 20, "fp32", return_iters=True)
+    _lib.set_option(_lib.OPT_LDPC_NO_BULK, 1)
+    try:
+        dec32r, out32r, it32r = ldpc_bp_decode_batch(llr.astype(np.float32), params, 20, "fp32", return_iters=True)
+    finally:
+        _lib.set_option(_lib.OPT_LDPC_NO_BULK, 0)
     assert torch.equal(dec32, dec32r) and torch.equal(it32, it32r)
     assert torch.equal(out32.view(torch.int32), out32r.view(torch.int32))
 

@@ -120,12 +120,13 @@ def test_full_size_properties_and_kernel_cross_check():
     _, xs = helpers.channel_frames(tr, rs, 4096, 1024, "soft", "cont", ebn0_db=2.0)
     xsf = torch.from_numpy(xs.astype(np.float32)).cuda()
     fast_s = viterbi_decode_batch(xsf, tr, None, "soft")
-    os.environ["CPB_VITERBI_FORCE_GENERIC"] = "1"
+    from commpy_b200 import _lib
+    _lib.set_option(_lib.OPT_VITERBI_FORCE_GENERIC, 1)
     try:
         gen = viterbi_decode_batch(xh, tr, None, "hard")
         gen_s = viterbi_decode_batch(xsf, tr, None, "soft")
     finally:
-        del os.environ["CPB_VITERBI_FORCE_GENERIC"]
+        _lib.set_option(_lib.OPT_VITERBI_FORCE_GENERIC, 0)
     assert torch.equal(fast, gen)
     assert (fast_s != gen_s).float().mean().item() <= 1e-4
 
@@ -211,3 +212,29 @@ def test_c2_shape_soft_vs_oracle():
     got = viterbi_decode_batch(x.astype(np.float32), tr, None, "soft")
     assert (got != want).mean() <= 1e-4
     assert abs(int((got != msgs).sum()) - int((want != msgs).sum())) <= 8
+
+
+def test_packed_hard_equals_unpacked():
+    """cpb_viterbi_decode_packed / _host_packed: 1 bit per bit in and out (numpy.packbits order) gives exactly the bits of
+    the byte-per-bit path, on the device and through the host pipeline, for every fast-path code and several depths."""
+    import torch
+    rs = np.random.RandomState(31)
+    for make in (helpers.k7, helpers.k7_wifi_quirk):
+        tr = make()
+        for nbits, term in ((1024, "cont"), (120, "cont"), (250, "term")):
+            _, x = helpers.channel_frames(tr, rs, 77, nbits, "hard", term, flip=0.05)
+            x = x.astype(np.uint8)
+            if x.shape[1] % 16:
+                continue
+            for tb in (None, 30, 10, 46):
+                want = oracle.viterbi_decode_batch(x.astype(np.float64), tr, tb, "hard", threads=4)
+                xp = np.packbits(x, axis=1)
+                got_h = viterbi_decode_batch(xp, tr, tb, "hard", packed=True)
+                assert got_h.shape == (77, want.shape[1] // 8)
+                assert np.array_equal(np.unpackbits(got_h, axis=1), want), (nbits, tb)
+                got_d = viterbi_decode_batch(torch.from_numpy(xp).cuda(), tr, tb, "hard", packed=True)
+                assert np.array_equal(got_d.cpu().numpy(), got_h)
+    with pytest.raises(NotImplementedError):
+        viterbi_decode_batch(np.packbits(x, axis=1), tr, 31, "hard", packed=True)
+    with pytest.raises(ValueError):
+        viterbi_decode_batch(np.zeros((4, 2048), np.uint8), helpers.k7(), None, "hard", out=np.zeros((4, 100), np.uint8))
