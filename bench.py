@@ -407,13 +407,13 @@ class TurboWorkload(Workload):
     def e2e_setup(self, torch):
         self.h = [t.cpu().pin_memory() for t in self.y]
         self.h_out = torch.empty((self.batch, self.N), dtype=torch.uint8).pin_memory()
+        self.h_np = [t.numpy() for t in self.h]
         return {"frames_per_call": self.batch, "h2d": 3 * self.batch * self.N * 4, "d2h": self.batch * self.N,
-                "api": "commpy_b200.channelcoding.turbo_decode_batch(pinned host arrays) + .cpu() of the decoded bits"}
+                "api": "commpy_b200.channelcoding.turbo_decode_batch_host(pinned host arrays) -> cpb_turbo_decode_host"}
 
     def e2e_step(self):
-        from commpy_b200.channelcoding import turbo_decode_batch
-        bits = turbo_decode_batch(self.h[0], self.h[1], self.h[2], self.trellis, self.s2, self.iters, self.il)
-        self.h_out.copy_(bits)
+        from commpy_b200.channelcoding import turbo_decode_batch_host
+        self.e2e_bits = turbo_decode_batch_host(self.h_np[0], self.h_np[1], self.h_np[2], self.trellis, self.s2, self.iters, self.il)
 
     def e2e_alt(self):
         return None
@@ -497,14 +497,13 @@ class LdpcWorkload(Workload):
 
     def e2e_setup(self, torch):
         self.h_llr = self.llr.cpu().pin_memory()
-        self.h_out = torch.empty((self.batch, self.n), dtype=torch.uint8).pin_memory()
+        self.h_np = self.h_llr.numpy()
         return {"frames_per_call": self.batch, "h2d": self.batch * self.n * 4, "d2h": self.batch * self.n,
-                "api": "commpy_b200.channelcoding.ldpc_bp_decode_batch(pinned host array) + .cpu() of the decisions"}
+                "api": "commpy_b200.channelcoding.ldpc_bp_decode_batch_host(pinned host array) -> cpb_ldpc_decode_host"}
 
     def e2e_step(self):
-        from commpy_b200.channelcoding import ldpc_bp_decode_batch
-        dec = ldpc_bp_decode_batch(self.h_llr, self.params, self.iters, "fp32", return_llrs=False)
-        self.h_out.copy_(dec)
+        from commpy_b200.channelcoding import ldpc_bp_decode_batch_host
+        self.e2e_dec = ldpc_bp_decode_batch_host(self.h_np, self.params, self.iters, "fp32", return_llrs=False)
 
     def e2e_alt(self):
         return None

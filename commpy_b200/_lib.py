@@ -21,10 +21,12 @@ SYMBOLS = [
     "cpb_strerror", "cpb_last_cuda_error", "cpb_version", "cpb_device_info", "cpb_set_option", "cpb_get_option",
     "cpb_trellis_create", "cpb_trellis_destroy", "cpb_trellis_fast_path",
     "cpb_viterbi_sizes", "cpb_viterbi_workspace_bytes", "cpb_viterbi_decode", "cpb_viterbi_decode_host", "cpb_viterbi_decode_packed", "cpb_viterbi_decode_host_packed",
-    "cpb_map_decode", "cpb_turbo_decode",
+    "cpb_viterbi_punctured_workspace_bytes", "cpb_viterbi_decode_punctured",
+    "cpb_map_workspace_bytes", "cpb_map_decode", "cpb_turbo_workspace_bytes", "cpb_turbo_decode",
+    "cpb_map_decode_host", "cpb_turbo_decode_host", "cpb_ldpc_decode_host", "cpb_demod_soft_host",
     "cpb_ldpc_create", "cpb_ldpc_destroy", "cpb_ldpc_workspace_bytes", "cpb_ldpc_minsum", "cpb_ldpc_sumproduct",
     "cpb_modem_create", "cpb_modem_destroy", "cpb_modem_is_separable", "cpb_demod_soft", "cpb_demod_hard",
-    "cpb_count_errors", "cpb_conv_link_tx",
+    "cpb_count_errors", "cpb_conv_link_tx", "cpb_conv_link_tx_punctured",
 ]
 
 _lib = None

@@ -12,7 +12,8 @@ import numpy as np
 from .. import _lib
 from ..utilities import bitarray2dec, dec2bitarray, decimal2bitarray
 
-__all__ = ["Trellis", "conv_encode", "viterbi_decode", "viterbi_decode_batch", "puncturing", "depuncturing"]
+__all__ = ["Trellis", "conv_encode", "viterbi_decode", "viterbi_decode_batch", "viterbi_decode_punctured_batch", "puncturing",
+           "depuncturing"]
 
 
 def _tap_bits(number, width, polynomial_format):
@@ -375,6 +376,40 @@ def viterbi_decode_batch(coded, trellis, tb_depth=None, decoding_type="hard", ou
                                      C.c_int64(n_in), int(tb_depth or 0), _lib.VITERBI_MODES[decoding_type],
                                      _lib.ptr(out))
     _lib.check(rc, "viterbi_decode")
+    return out
+
+
+def viterbi_decode_punctured_batch(llr, trellis, punct_vec, shouldbe, tb_depth=None, decoding_type="soft"):
+    """depuncturing(row, punct_vec, shouldbe) + viterbi_decode(..., decoding_type) for a batch of PUNCTURED rows in one kernel
+    (cpb_viterbi_decode_punctured: the zeros of convcode.py:777-804 are inserted in the kernel's load, nothing is
+    materialised).  llr: (batch, n_kept) float32 CUDA tensor or array.  Returns a (batch, L) uint8 CUDA tensor.
+    Trellises without a register-resident kernel take the two-step route (host depuncturing mirror + viterbi_decode_batch)."""
+    if decoding_type not in ("soft", "unquantized"):
+        raise ValueError("punctured decoding takes soft values ('soft' or 'unquantized')")
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    if hasattr(llr, "data_ptr"):
+        x = (llr if llr.is_cuda else llr.cuda()).to(torch.float32).contiguous()
+    else:
+        x = torch.from_numpy(np.ascontiguousarray(llr, dtype=np.float32)).cuda()
+    if x.dim() != 2:
+        raise ValueError("llr must be (batch, n_kept)")
+    pv = np.ascontiguousarray(punct_vec, dtype=np.int32)
+    batch, n_kept = x.shape
+    L, T = _sizes(trellis, int(shouldbe))
+    _check_depth(trellis, L, T, tb_depth)
+    handle = _trellis_handle(trellis)
+    out = torch.empty((batch, L), dtype=torch.uint8, device=x.device)
+    rc = lib.cpb_viterbi_decode_punctured(handle, _lib.ptr(x), C.c_int64(batch), C.c_int64(n_kept), _lib.ptr(pv), int(len(pv)),
+                                          C.c_int64(int(shouldbe)), int(tb_depth or 0), _lib.VITERBI_MODES[decoding_type],
+                                          _lib.ptr(out), C.c_void_p(0), C.c_size_t(0), _lib.stream_ptr(torch))
+    if rc == _lib.CPB_EUNSUPPORTED:
+        rows = x.cpu().numpy()
+        dep = np.stack([depuncturing(r, pv, int(shouldbe)) for r in rows]).astype(np.float32)
+        return viterbi_decode_batch(torch.from_numpy(dep).cuda(), trellis, tb_depth, decoding_type)
+    if rc == _lib.CPB_EINVAL and n_kept < int(np.sum(pv[np.arange(int(shouldbe)) % len(pv)] == 1)):
+        raise IndexError("index %d is out of bounds for axis 0 with size %d" % (n_kept, n_kept))
+    _lib.check(rc, "viterbi_decode (punctured)")
     return out
 
 

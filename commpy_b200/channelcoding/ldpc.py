@@ -137,6 +137,35 @@ def ldpc_bp_decode_batch(llr, ldpc_code_params, n_iters, precision="fp32", retur
     return res[0] if len(res) == 1 else tuple(res)
 
 
+def ldpc_bp_decode_batch_host(llr, ldpc_code_params, n_iters, precision="fp32", return_llrs=True, return_iters=False,
+                              decoder_algorithm="MSA"):
+    """The same for a HOST array through the pipelined host entry point (cpb_ldpc_decode_host): `llr` is a C-contiguous
+    numpy (batch, n) array of the precision's dtype and is clipped IN PLACE to +-500 like the reference (ldpc.py:186).
+    Returns numpy arrays: dec (batch, n) uint8 [, out_llrs] [, iterations int32]."""
+    _lib.require_cuda()
+    if decoder_algorithm not in ("MSA", "SPA"):
+        raise NameError('Please input a valid decoder_algorithm string (meanning "SPA" or "MSA").')
+    handle, n = _ldpc_handle(ldpc_code_params)
+    dt = np.float64 if precision == "fp64" else np.float32
+    x = llr if (isinstance(llr, np.ndarray) and llr.dtype == dt and llr.flags["C_CONTIGUOUS"]) else np.ascontiguousarray(llr, dtype=dt)
+    if x.ndim != 2 or x.shape[1] != n:
+        raise ValueError("llr must be (batch, n_vnodes)")
+    batch = x.shape[0]
+    dec = np.empty((batch, n), dtype=np.uint8)
+    out = np.empty((batch, n), dtype=dt) if return_llrs else None
+    iters = np.empty((batch,), dtype=np.int32) if return_iters else None
+    rc = _lib.load().cpb_ldpc_decode_host(handle, 0 if decoder_algorithm == "MSA" else 1, _lib.ptr(x),
+                                          _lib.LDPC_FP64 if precision == "fp64" else _lib.LDPC_FP32, C.c_int64(batch),
+                                          int(n_iters), _lib.ptr(dec), _lib.ptr(out), _lib.ptr(iters))
+    _lib.check(rc, "ldpc_bp_decode")
+    res = [dec]
+    if return_llrs:
+        res.append(out)
+    if return_iters:
+        res.append(iters)
+    return res[0] if len(res) == 1 else tuple(res)
+
+
 def ldpc_bp_decode(llr_vec, ldpc_code_params, decoder_algorithm, n_iters, precision="fp64"):
     """Drop-in for commpy.channelcoding.ldpc_bp_decode (ldpc.py:144-254), 'MSA' and 'SPA' algorithms.
 
@@ -153,10 +182,10 @@ def ldpc_bp_decode(llr_vec, ldpc_code_params, decoder_algorithm, n_iters, precis
         llr_vec.clip(-_llr_max, _llr_max, llr_vec)            # in place, ldpc.py:186
     _, n = _ldpc_handle(ldpc_code_params)
     n_blocks = llr_vec.size // n
-    dec, out = ldpc_bp_decode_batch(llr_vec.reshape(n_blocks, n), ldpc_code_params, n_iters, precision,
-                                    decoder_algorithm=decoder_algorithm)
-    dec_word = dec.cpu().numpy().reshape(-1).reshape(-1, n_blocks, order="F").squeeze().astype(np.int8)
-    out_llrs = out.cpu().numpy().astype(np.float64).reshape(-1).reshape(-1, n_blocks, order="F").squeeze()
+    dec, out = ldpc_bp_decode_batch_host(llr_vec.reshape(n_blocks, n), ldpc_code_params, n_iters, precision,
+                                         decoder_algorithm=decoder_algorithm)
+    dec_word = dec.reshape(-1).reshape(-1, n_blocks, order="F").squeeze().astype(np.int8)
+    out_llrs = out.astype(np.float64).reshape(-1).reshape(-1, n_blocks, order="F").squeeze()
     return dec_word, out_llrs
 
 

@@ -1,10 +1,13 @@
 """Turbo codes: encoder (host) and BCJR / turbo decoding on the GPU.
 
 Mirror of commpy/channelcoding/turbo.py.  `map_decode` / `turbo_decode` run in CUDA
-(commpy_b200/csrc/bcjr.cu) through `cpb_map_decode` / `cpb_turbo_decode`; there is no CPU decode path.
-The kernels use the log-domain exact max* instead of the reference's renormalised probabilities -- the
-same algorithm (log-MAP), float32 instead of float64: LLRs agree to ~1e-5 where the reference is finite
-(it returns +-inf once its exponentials underflow; the GPU path stays finite there).
+(commpy_b200/csrc/bcjr.cu) through `cpb_map_decode[_host]` / `cpb_turbo_decode[_host]`; there is no CPU decode path.
+The hot kernel works, like the reference, with probabilities renormalised every step (float32 instead of float64,
+branch weights taken relative to the step's best symbol so nothing underflows); one thread owns a window of 1024
+trellis steps of a frame and warms its recursions up over 96 steps of the neighbouring windows (<= 3.4e-7 on the LLRs
+against the reference's full-frame recursion).  Unaligned frame lengths and other trellises take the log-domain exact
+max* kernels.  LLRs agree to ~1e-5 where the reference is finite (it returns +-inf once its exponentials underflow; the
+GPU path stays finite there).
 """
 import ctypes as C
 
@@ -13,7 +16,8 @@ import numpy as np
 from .. import _lib
 from .convcode import _trellis_handle, conv_encode
 
-__all__ = ["turbo_encode", "map_decode", "turbo_decode", "map_decode_batch", "turbo_decode_batch"]
+__all__ = ["turbo_encode", "map_decode", "turbo_decode", "map_decode_batch", "turbo_decode_batch", "map_decode_batch_host",
+           "turbo_decode_batch_host"]
 
 
 def turbo_encode(msg_bits, trellis1, trellis2, interleaver):
@@ -51,9 +55,63 @@ def map_decode_batch(sys_symbols, non_sys_symbols, trellis, noise_variance, L_in
     bits = torch.empty((batch, N), dtype=torch.uint8, device=s.device)
     rc = _lib.load().cpb_map_decode(_trellis_handle(trellis), _lib.ptr(s), _lib.ptr(p), _lib.ptr(la),
                                     C.c_int64(batch), C.c_int64(N), C.c_float(noise_variance),
-                                    1 if mode == "decode" else 0, _lib.ptr(L), _lib.ptr(bits), _lib.stream_ptr(torch))
+                                    1 if mode == "decode" else 0, _lib.ptr(L), _lib.ptr(bits), C.c_void_p(0), C.c_size_t(0),
+                                    _lib.stream_ptr(torch))
     _lib.check(rc, "map_decode")
     return L, bits
+
+
+def map_decode_batch_host(sys_symbols, non_sys_symbols, trellis, noise_variance, L_int, mode="decode"):
+    """Batched MAP decoder for HOST arrays through the pipelined host entry point (cpb_map_decode_host):
+    (batch, N) float arrays -> (L (batch, N) float32, bits (batch, N) uint8) numpy arrays."""
+    _lib.require_cuda()
+    s = np.ascontiguousarray(sys_symbols, dtype=np.float32)
+    p = np.ascontiguousarray(non_sys_symbols, dtype=np.float32)
+    la = np.ascontiguousarray(L_int, dtype=np.float32)
+    if s.ndim != 2 or s.shape != p.shape or s.shape != la.shape:
+        raise ValueError("sys_symbols, non_sys_symbols and L_int must share the shape (batch, N)")
+    batch, N = s.shape
+    L = np.empty((batch, N), dtype=np.float32)
+    bits = np.empty((batch, N), dtype=np.uint8)
+    rc = _lib.load().cpb_map_decode_host(_trellis_handle(trellis), _lib.ptr(s), _lib.ptr(p), _lib.ptr(la), C.c_int64(batch),
+                                         C.c_int64(N), C.c_float(noise_variance), 1 if mode == "decode" else 0,
+                                         _lib.ptr(L), _lib.ptr(bits))
+    _lib.check(rc, "map_decode")
+    return L, bits
+
+
+def turbo_decode_batch_host(sys_symbols, non_sys_symbols_1, non_sys_symbols_2, trellis, noise_variance,
+                            number_iterations, interleaver, L_int=None):
+    """Batched turbo decoder for HOST arrays through the pipelined host entry point (cpb_turbo_decode_host):
+    (batch, N) float arrays -> (batch, N) uint8 numpy array."""
+    _lib.require_cuda()
+    s = np.ascontiguousarray(sys_symbols, dtype=np.float32)
+    p1 = np.ascontiguousarray(non_sys_symbols_1, dtype=np.float32)
+    p2 = np.ascontiguousarray(non_sys_symbols_2, dtype=np.float32)
+    if s.ndim != 2 or s.shape != p1.shape or s.shape != p2.shape:
+        raise ValueError("the three symbol streams must share the shape (batch, N)")
+    batch, N = s.shape
+    perm = _checked_perm(interleaver, N)
+    la = None if L_int is None else np.ascontiguousarray(L_int, dtype=np.float32)
+    bits = np.empty((batch, N), dtype=np.uint8)
+    rc = _lib.load().cpb_turbo_decode_host(_trellis_handle(trellis), _lib.ptr(s), _lib.ptr(p1), _lib.ptr(p2), _lib.ptr(perm),
+                                           C.c_int64(batch), C.c_int64(N), C.c_float(noise_variance), int(number_iterations),
+                                           _lib.ptr(la), _lib.ptr(bits))
+    _lib.check(rc, "turbo_decode")
+    return bits
+
+
+def _checked_perm(interleaver, N):
+    """p_array as int32, validated: the kernels gather / scatter through it, so it must be a permutation of 0..N-1 (the
+    reference raises IndexError on an out-of-range entry; a repeated entry would leave part of the output unwritten)"""
+    perm_np = np.ascontiguousarray(interleaver.p_array, dtype=np.int64)
+    if len(perm_np) != N:
+        raise ValueError("interleaver length does not match the frame length")
+    if N and (perm_np.min() < 0 or perm_np.max() >= N):
+        raise IndexError("interleaver.p_array holds an index outside [0, %d)" % N)
+    if np.unique(perm_np).size != N:
+        raise ValueError("interleaver.p_array is not a permutation")
+    return perm_np.astype(np.int32)
 
 
 def map_decode(sys_symbols, non_sys_symbols, trellis, noise_variance, L_int, mode="decode"):
@@ -61,9 +119,9 @@ def map_decode(sys_symbols, non_sys_symbols, trellis, noise_variance, L_int, mod
 
     `L_ext` is, as in the reference, the full a-posteriori LLR  L_int + log(app1/app0)  (:145-146);
     `decoded_bits` is (L_ext > 0) in mode 'decode' and zeros in mode 'compute' (:148-152)."""
-    L, bits = map_decode_batch(np.asarray(sys_symbols)[None, :], np.asarray(non_sys_symbols)[None, :], trellis,
-                               noise_variance, np.asarray(L_int)[None, :], mode)
-    return [L[0].cpu().numpy().astype(np.float64), bits[0].cpu().numpy().astype("int")]
+    L, bits = map_decode_batch_host(np.asarray(sys_symbols)[None, :], np.asarray(non_sys_symbols)[None, :], trellis,
+                                    noise_variance, np.asarray(L_int)[None, :], mode)
+    return [L[0].astype(np.float64), bits[0].astype("int")]
 
 
 def turbo_decode_batch(sys_symbols, non_sys_symbols_1, non_sys_symbols_2, trellis, noise_variance,
@@ -76,15 +134,14 @@ def turbo_decode_batch(sys_symbols, non_sys_symbols_1, non_sys_symbols_2, trelli
     if s.dim() != 2 or s.shape != p1.shape or s.shape != p2.shape:
         raise ValueError("the three symbol streams must share the shape (batch, N)")
     batch, N = s.shape
-    perm_np = np.ascontiguousarray(interleaver.p_array, dtype=np.int32)
-    if len(perm_np) != N:
-        raise ValueError("interleaver length does not match the frame length")
+    perm_np = _checked_perm(interleaver, N)
     perm = torch.from_numpy(perm_np).cuda()
     la = None if L_int is None else _dev_f32(L_int, torch)
     bits = torch.empty((batch, N), dtype=torch.uint8, device=s.device)
     rc = _lib.load().cpb_turbo_decode(_trellis_handle(trellis), _lib.ptr(s), _lib.ptr(p1), _lib.ptr(p2), _lib.ptr(perm),
                                       C.c_int64(batch), C.c_int64(N), C.c_float(noise_variance),
-                                      int(number_iterations), _lib.ptr(la), _lib.ptr(bits), _lib.stream_ptr(torch))
+                                      int(number_iterations), _lib.ptr(la), _lib.ptr(bits), C.c_void_p(0), C.c_size_t(0),
+                                      _lib.stream_ptr(torch))
     _lib.check(rc, "turbo_decode")
     return bits
 
@@ -96,7 +153,7 @@ def turbo_decode(sys_symbols, non_sys_symbols_1, non_sys_symbols_2, trellis, noi
     Keeps the reference's loop exactly, including the systematic double counting (only the prior is removed
     from each decoder's output, :318 and :328) and the final de-interleave of decoder 2's hard decisions (:331)."""
     la = None if L_int is None else np.asarray(L_int)[None, :]
-    bits = turbo_decode_batch(np.asarray(sys_symbols)[None, :], np.asarray(non_sys_symbols_1)[None, :],
-                              np.asarray(non_sys_symbols_2)[None, :], trellis, noise_variance, number_iterations,
-                              interleaver, la)
-    return bits[0].cpu().numpy().astype("int")
+    bits = turbo_decode_batch_host(np.asarray(sys_symbols)[None, :], np.asarray(non_sys_symbols_1)[None, :],
+                                   np.asarray(non_sys_symbols_2)[None, :], trellis, noise_variance, number_iterations,
+                                   interleaver, la)
+    return bits[0].astype("int")

@@ -961,9 +961,30 @@ static int64_t chunk_frames(int64_t batch, int N, int S)
 
 extern "C" {
 
+int cpb_map_workspace_bytes(const cpbTrellis *t, int64_t batch, int64_t N, size_t *bytes)
+{
+    int S = 0;
+    int rc = bcjr::check_trellis(t, &S);
+    if (rc) return rc;
+    if (!bytes || batch < 0 || N < 1 || N > (1 << 24)) return CPB_EINVAL;
+    *bytes = batch ? bcjr::beta_floats(bcjr::chunk_frames(batch, (int)N, S), (int)N, S) * sizeof(float) : 0;
+    return CPB_OK;
+}
+
+int cpb_turbo_workspace_bytes(const cpbTrellis *t, int64_t batch, int64_t N, size_t *bytes)
+{
+    int S = 0;
+    int rc = bcjr::check_trellis(t, &S);
+    if (rc) return rc;
+    if (!bytes || batch < 0 || N < 1 || N > (1 << 24)) return CPB_EINVAL;
+    const int64_t Fc = batch ? bcjr::chunk_frames(batch, (int)N, S) : 0;
+    *bytes = batch ? (bcjr::beta_floats(Fc, (int)N, S) + 5 * (size_t)Fc * N) * sizeof(float) + (size_t)Fc * N + 256 : 0;
+    return CPB_OK;
+}
+
 int cpb_map_decode(const cpbTrellis *t, const float *sys_dev, const float *par_dev, const float *L_int_dev,
                    int64_t batch, int64_t N, float noise_variance, int mode, float *L_out_dev, uint8_t *bits_out_dev,
-                   void *stream)
+                   void *workspace_dev, size_t workspace_bytes, void *stream)
 {
     int S = 0;
     int rc = bcjr::check_trellis(t, &S);
@@ -974,7 +995,7 @@ int cpb_map_decode(const cpbTrellis *t, const float *sys_dev, const float *par_d
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t Fc = bcjr::chunk_frames(batch, (int)N, S);
     Scratch ws;
-    rc = ws.acquire(nullptr, 0, bcjr::beta_floats(Fc, (int)N, S) * sizeof(float), st);
+    rc = ws.acquire(workspace_dev, workspace_bytes, bcjr::beta_floats(Fc, (int)N, S) * sizeof(float), st);
     if (rc) return rc;
     for (int64_t f0 = 0; f0 < batch && rc == CPB_OK; f0 += Fc) {
         const int64_t nb = std::min<int64_t>(Fc, batch - f0);
@@ -988,7 +1009,7 @@ int cpb_map_decode(const cpbTrellis *t, const float *sys_dev, const float *par_d
 
 int cpb_turbo_decode(const cpbTrellis *t, const float *sys_dev, const float *par1_dev, const float *par2_dev,
                      const int32_t *perm_dev, int64_t batch, int64_t N, float noise_variance, int n_iter,
-                     const float *L_int0_dev, uint8_t *bits_out_dev, void *stream)
+                     const float *L_int0_dev, uint8_t *bits_out_dev, void *workspace_dev, size_t workspace_bytes, void *stream)
 {
     int S = 0;
     int rc = bcjr::check_trellis(t, &S);
@@ -1002,7 +1023,7 @@ int cpb_turbo_decode(const cpbTrellis *t, const float *sys_dev, const float *par
     const int64_t Fc = bcjr::chunk_frames(batch, (int)N, S);
     const size_t nbeta = bcjr::beta_floats(Fc, (int)N, S), nvec = (size_t)Fc * N;
     Scratch ws;
-    rc = ws.acquire(nullptr, 0, (nbeta + 5 * nvec) * sizeof(float) + nvec + 256, st);
+    rc = ws.acquire(workspace_dev, workspace_bytes, (nbeta + 5 * nvec) * sizeof(float) + nvec + 256, st);
     if (rc) return rc;
     float *beta = reinterpret_cast<float *>(ws.ptr);
     float *sys_i = beta + nbeta, *La1 = sys_i + nvec, *La2 = La1 + nvec, *L1 = La2 + nvec, *L2 = L1 + nvec;
@@ -1020,9 +1041,16 @@ int cpb_turbo_decode(const cpbTrellis *t, const float *sys_dev, const float *par
         const bool rows = (size_t)N * sizeof(float) <= 96 * 1024;
         const size_t rsm = (size_t)N * sizeof(float);
         if (rows) {
-            cudaFuncSetAttribute(bcjr::row_gather_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
-            cudaFuncSetAttribute(bcjr::row_scatter_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
-            cudaFuncSetAttribute(bcjr::row_scatter_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)N);
+            static thread_local size_t opted[64] = {0};          // per device: largest row already opted in
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (dev < 0 || dev >= 64) dev = 0;
+            if (opted[dev] < rsm) {
+                cudaFuncSetAttribute(bcjr::row_gather_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
+                cudaFuncSetAttribute(bcjr::row_scatter_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
+                cudaFuncSetAttribute(bcjr::row_scatter_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)N);
+                opted[dev] = rsm;
+            }
         }
         if (rows) bcjr::row_gather_sub_kernel<<<(unsigned)nb, 256, rsm, st>>>(sy, nullptr, perm_dev, (int)N, sys_i);
         else bcjr::gather_sub_kernel<<<eg, 256, 0, st>>>(sy, nullptr, perm_dev, nb, (int)N, sys_i);          // :310

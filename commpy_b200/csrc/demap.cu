@@ -18,10 +18,12 @@
 #include <vector>
 
 #include "common.cuh"
+#include "handles.cuh"
 
 using namespace cpb;
 
 struct cpbModem {
+    cpb::PipeCtx pipe;             // host-buffer pipeline of cpb_demod_*_host calls made with this handle
     int M, nb;
     float2 *cst_dev = nullptr;     // M points
     int separable = 0;
@@ -211,6 +213,8 @@ __global__ void __launch_bounds__(256) demod_hard_kernel(const float2 *__restric
 }  // namespace demap
 
 // accessor for the other translation units (not part of the C-ABI)
+cpb::PipeCtx &cpb_modem_pipe(cpbModem *m) { return m->pipe; }
+
 void cpb_modem_info(const cpbModem *m, int *M, int *nb, const float **cst_dev)
 {
     *M = m->M; *nb = m->nb; *cst_dev = reinterpret_cast<const float *>(m->cst_dev);

@@ -26,15 +26,20 @@
 #include <vector>
 
 #include "common.cuh"
+#include "handles.cuh"
 
 using namespace cpb;
 
 struct cpbLdpc {
+    cpb::PipeCtx pipe;                                  // host-buffer pipeline of cpb_ldpc_*_host calls made with this handle
     int m, n, nnz;
     int max_row_deg, max_col_deg;
     int32_t *row_ptr = nullptr, *col_idx = nullptr;     // CSR
     int32_t *col_ptr = nullptr, *col_edge = nullptr;    // CSC: edge ids (CSR positions) of a column, ascending check
 };
+
+cpb::PipeCtx &cpb_ldpc_pipe(cpbLdpc *h) { return h->pipe; }
+void cpb_ldpc_dims(const cpbLdpc *h, int *m, int *n) { *m = h->m; *n = h->n; }
 
 namespace ldpc {
 

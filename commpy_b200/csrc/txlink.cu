@@ -39,6 +39,8 @@ struct Params {
     uint32_t seed_lo, seed_hi;
     float sigma;              // per real component
     int spt;                  // symbols per thread
+    uint32_t punct_mask;      // puncturing pattern over the coded stream (bit c mod punct_len set = keep), convcode.py:752-774
+    int punct_len, punct_ones;
     int64_t chunks;           // threads per frame
     const float2 *cst;
     uint8_t *msg;
@@ -81,7 +83,9 @@ __global__ void __launch_bounds__(128) conv_link_tx_kernel(const Params p)
     const uint32_t f_lo = (uint32_t)fg, f_hi = (uint32_t)(fg >> 32);
     const int64_t s0 = ch * p.spt;
     const int64_t s1 = min(s0 + (int64_t)p.spt, p.nsym);
-    int64_t i = s0 * p.nb / p.n;                             // first information bit (s0 * nb is a multiple of n)
+    // first information bit: s0 * nb kept bits are whole puncturing periods (punct_ones kept out of punct_len coded bits)
+    int64_t i = (s0 * p.nb / p.punct_ones) * p.punct_len / p.n;
+    int cpos = 0;
 
     uint32_t blk_id = 0xffffffffu;
     uint4 blk = make_uint4(0, 0, 0, 0);
@@ -118,8 +122,10 @@ __global__ void __launch_bounds__(128) conv_link_tx_kernel(const Params p)
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            if (j < p.n) acc = (acc << 1) | (uint64_t)(__popc(reg & p.g[j]) & 1);
-        nacc += p.n;
+            if (j < p.n) {
+                if ((p.punct_mask >> cpos) & 1u) { acc = (acc << 1) | (uint64_t)(__popc(reg & p.g[j]) & 1); ++nacc; }
+                cpos = (cpos + 1 == p.punct_len) ? 0 : cpos + 1;
+            }
         ++i;
         while (nacc >= p.nb && sym < s1) {
             nacc -= p.nb;
@@ -151,9 +157,9 @@ static int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
 
 }  // namespace txlink
 
-extern "C" int cpb_conv_link_tx(const cpbTrellis *t, const cpbModem *m, int64_t frames, int64_t frame_bits,
-                                uint64_t seed, int64_t first_frame, float noise_sigma, uint8_t *msg_dev, float *y_dev,
-                                void *stream)
+static int conv_link_tx_impl(const cpbTrellis *t, const cpbModem *m, int64_t frames, int64_t frame_bits, uint64_t seed,
+                             int64_t first_frame, float noise_sigma, const int32_t *punct_vec, int punct_len,
+                             uint8_t *msg_dev, float *y_dev, void *stream)
 {
     if (!t || !m || frames < 0 || frame_bits < 1 || first_frame < 0) return CPB_EINVAL;
     if (frames == 0) return CPB_OK;
@@ -188,13 +194,29 @@ extern "C" int cpb_conv_link_tx(const cpbTrellis *t, const cpbModem *m, int64_t 
     const float *cst;
     cpb_modem_info(m, &Mc, &nb, &cst);
     if (nb < 1 || nb > 16) return CPB_EUNSUPPORTED;
-    if ((frame_bits * n) % nb) return CPB_EINVAL;            // the frame must fill whole symbols
+    // puncturing pattern over the coded stream; none = every bit of a period of n kept
+    if (punct_vec) {
+        if (punct_len < 1 || punct_len > 32 || (punct_len % n) != 0) return CPB_EUNSUPPORTED;
+        for (int i = 0; i < punct_len; ++i)
+            if (punct_vec[i] == 1) { p.punct_mask |= 1u << i; ++p.punct_ones; }
+        p.punct_len = punct_len;
+        if (p.punct_ones == 0) return CPB_EINVAL;
+    } else {
+        p.punct_len = n; p.punct_ones = n; p.punct_mask = (1u << n) - 1u;
+    }
+    const int64_t coded = frame_bits * n;
+    const int64_t kept = (coded / p.punct_len) * p.punct_ones +
+                         __builtin_popcount(p.punct_mask & ((1u << (coded % p.punct_len)) - 1u));
+    if (kept % nb) return CPB_EINVAL;                        // the frame must fill whole symbols
     p.n = n; p.mem = mem; p.nb = nb; p.Mc = Mc;
-    p.frames = frames; p.frame_bits = frame_bits; p.nsym = frame_bits * n / nb;
+    p.frames = frames; p.frame_bits = frame_bits; p.nsym = kept / nb;
     p.first_frame = first_frame;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
     p.sigma = noise_sigma;
-    p.spt = 32 * (n / txlink::gcd_int(32 * nb, n));          // even, and spt * nb is a multiple of n
+    // symbols per thread: even (noise comes in pairs) and a whole number of puncturing periods, about 32
+    int unit = p.punct_ones / txlink::gcd_int(p.punct_ones, nb);
+    if (unit & 1) unit *= 2;
+    p.spt = unit * ((32 + unit - 1) / unit);
     p.chunks = ceil_div(p.nsym, (int64_t)p.spt);
     p.cst = reinterpret_cast<const float2 *>(cst);
     p.msg = msg_dev;
@@ -204,4 +226,21 @@ extern "C" int cpb_conv_link_tx(const cpbTrellis *t, const cpbModem *m, int64_t 
     txlink::conv_link_tx_kernel<<<grid, 128, (size_t)Mc * sizeof(float2), (cudaStream_t)stream>>>(p);
     CPB_LAUNCH_CHECK();
     return CPB_OK;
+}
+
+extern "C" int cpb_conv_link_tx(const cpbTrellis *t, const cpbModem *m, int64_t frames, int64_t frame_bits,
+                                uint64_t seed, int64_t first_frame, float noise_sigma, uint8_t *msg_dev, float *y_dev,
+                                void *stream)
+{
+    return conv_link_tx_impl(t, m, frames, frame_bits, seed, first_frame, noise_sigma, nullptr, 0, msg_dev, y_dev, stream);
+}
+
+extern "C" int cpb_conv_link_tx_punctured(const cpbTrellis *t, const cpbModem *m, int64_t frames, int64_t frame_bits,
+                                          uint64_t seed, int64_t first_frame, float noise_sigma,
+                                          const int32_t *punct_vec_host, int punct_len, uint8_t *msg_dev, float *y_dev,
+                                          void *stream)
+{
+    if (!punct_vec_host) return CPB_EINVAL;
+    return conv_link_tx_impl(t, m, frames, frame_bits, seed, first_frame, noise_sigma, punct_vec_host, punct_len, msg_dev,
+                             y_dev, stream);
 }

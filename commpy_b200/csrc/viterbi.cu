@@ -116,6 +116,11 @@ struct Params {
     int out_vec8;                // 1: rows of out are 8-byte aligned; 2: out is bit-packed (np.packbits order), L/8 bytes per row
     int in_aligned;              // 1: rows of coded are 4-byte (u8) / 16-byte (f32) aligned
     uint32_t met_mask;           // metric bits of a key, passed at run time so the key refresh stays one LOP3
+    // punctured float input (IOP = 2): row of n_kept values; coded position c holds the next kept value when bit
+    // (c mod punct_len) of punct_mask is set, else the erasure 0.0 (convcode.py:777-804)
+    uint32_t punct_mask;
+    int punct_len;
+    int64_t n_kept;
 };
 
 template <int PACK> struct KeyOps;
@@ -512,6 +517,8 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
     // received values of the pair of steps (2 pr + 1, 2 pr + 2)
     //   hard: the 4 coded bytes of frame A and of frame B;  float: the 4 raw values
     struct Raw { uint32_t w[(PACK == 2) ? 2 : 4]; };
+    int pc_pos = 0;
+    int64_t pc_idx = 0;
     auto load_pair = [&](int pr) {
         Raw r;
         if (PACK == 2) {
@@ -542,8 +549,20 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
         } else {
             const uint32_t pb = __float_as_uint(padq);
             r.w[0] = r.w[1] = r.w[2] = r.w[3] = pb;
-            const float *row = cf + fr[0] * p.n_in;
-            if (p.in_aligned && pr < npairs_in) {
+            const float *row = cf + fr[0] * (IOP == 2 ? p.n_kept : p.n_in);
+            if (IOP == 2) {
+                // depuncturing fused into the load: the queue asks for the pairs in order, so the position in the
+                // puncturing period and in the punctured row are running counters
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    if (2 * pr + 1 + (h >> 1) <= p.L) {
+                        float v = 0.0f;                                  // erased position (convcode.py:796-799)
+                        if ((p.punct_mask >> pc_pos) & 1u) { v = __ldg(row + pc_idx); ++pc_idx; }
+                        pc_pos = (pc_pos + 1 == p.punct_len) ? 0 : pc_pos + 1;
+                        r.w[h] = __float_as_uint(v);
+                    }
+                }
+            } else if (p.in_aligned && pr < npairs_in) {
                 const float4 v = __ldg(reinterpret_cast<const float4 *>(row) + pr);
                 r.w[0] = __float_as_uint(v.x); r.w[1] = __float_as_uint(v.y); r.w[2] = __float_as_uint(v.z); r.w[3] = __float_as_uint(v.w);
             } else {
@@ -718,6 +737,9 @@ __global__ void __launch_bounds__(BD) viterbi_fast_kernel_hard_packed(const Para
 // soft / unquantized: one frame per thread, 32-bit keys
 template <class CODE>
 __global__ void __launch_bounds__(BD, 12) viterbi_fast_kernel_soft(const Params p) { viterbi_fast_body<CODE, 1, 2, 0>(p); }
+// the same on punctured rows: depuncturing (convcode.py:777-804) happens in the load
+template <class CODE>
+__global__ void __launch_bounds__(BD, 12) viterbi_fast_kernel_soft_punct(const Params p) { viterbi_fast_body<CODE, 1, 2, 2>(p); }
 
 // Per-frame power-of-two scale for float input: the largest |value| of the frame (after the +-500 clip in 'soft'
 // mode, convcode.py:718-719; including the -1 padding of 'unquantized', :729-732) maps to at most 2^QBITS.
@@ -757,8 +779,9 @@ template <class CODE, int PACK, int IOP = 0>
 static int launch(const Params &p, cudaStream_t st)
 {
     const size_t smem = smem_bytes(p.RB, p.TBB, PACK);
-    void (*kern)(const Params) = IOP ? viterbi_fast_kernel_hard_packed<CODE>
-                                     : (PACK == 2) ? viterbi_fast_kernel_hard<CODE> : viterbi_fast_kernel_soft<CODE>;
+    void (*kern)(const Params) = (IOP == 1) ? viterbi_fast_kernel_hard_packed<CODE>
+                               : (IOP == 2) ? viterbi_fast_kernel_soft_punct<CODE>
+                               : (PACK == 2) ? viterbi_fast_kernel_hard<CODE> : viterbi_fast_kernel_soft<CODE>;
     static thread_local size_t attr_set[64] = {0};       // per device: largest dynamic smem size already opted in
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1015,6 +1038,12 @@ static size_t generic_chunk(const cpbTrellis *t, int64_t batch, int64_t T, int64
 
 static int launch_fast(const cpbTrellis *t, const fast::Params &p, int pack, int packed_io, cudaStream_t st)
 {
+    if (packed_io == 2) {
+        if (t->fast_id == 1) return fast::launch<Code133_171, 1, 2>(p, st);
+        if (t->fast_id == 2) return fast::launch<Code171_133, 1, 2>(p, st);
+        if (t->fast_id == 3) return fast::launch<Code5_43, 1, 2>(p, st);
+        return fast::launch<Code5_7, 1, 2>(p, st);
+    }
     if (packed_io) {
         if (t->fast_id == 1) return fast::launch<Code133_171, 2, 1>(p, st);
         if (t->fast_id == 2) return fast::launch<Code171_133, 2, 1>(p, st);
@@ -1162,6 +1191,62 @@ int cpb_viterbi_decode_packed(const cpbTrellis *t, const uint8_t *coded_packed_d
     p.met_mask = ~fast::KeyOps<2>::FMASK;
     if (fast::smem_bytes(p.RB, p.TBB, 2) > dp.smem_optin) return CPB_EUNSUPPORTED;
     return launch_fast(t, p, 2, 1, (cudaStream_t)stream);
+}
+
+
+int cpb_viterbi_punctured_workspace_bytes(int64_t batch, size_t *bytes)
+{
+    if (!bytes || batch < 0) return CPB_EINVAL;
+    *bytes = 256 + (size_t)batch * sizeof(float);
+    return CPB_OK;
+}
+
+int cpb_viterbi_decode_punctured(const cpbTrellis *t, const float *llr_punct_dev, int64_t batch, int64_t n_kept,
+                                 const int32_t *punct_vec_host, int punct_len, int64_t n_depunct, int tb_depth, int mode,
+                                 uint8_t *out_bits_dev, void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    if (mode != CPB_VITERBI_SOFT && mode != CPB_VITERBI_UNQUANTIZED) return CPB_EINVAL;
+    if (t && batch == 0) return CPB_OK;
+    if (!t || !llr_punct_dev || !out_bits_dev || !punct_vec_host || batch < 0 || n_kept < 0 || n_depunct <= 0) return CPB_EINVAL;
+    if (punct_len < 1 || punct_len > 32) return CPB_EUNSUPPORTED;
+    uint32_t mask = 0;
+    int ones = 0;
+    for (int i = 0; i < punct_len; ++i)
+        if (punct_vec_host[i] == 1) { mask |= 1u << i; ++ones; }
+    // values the depuncturing consumes (convcode.py:796-799 indexes the punctured array: IndexError when it is too short)
+    const int64_t need = (n_depunct / punct_len) * ones + __builtin_popcount(mask & ((1u << (n_depunct % punct_len)) - 1u));
+    if (need > n_kept) return CPB_EINVAL;
+    int64_t L, T;
+    cpb_viterbi_sizes(t, n_depunct, &L, &T);
+    const int D = resolve_depth(t, L, tb_depth);
+    if (L <= 0 || D < 2 || T < D - 1 || T > (1 << 24)) return CPB_EINVAL;
+    if (!use_fast(t, D, mode, CPB_F32)) return CPB_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const DeviceProps &dp = device_props();
+    fast::Params p{};
+    p.coded = llr_punct_dev; p.n_in = n_depunct; p.batch = batch;
+    p.L = (int)L; p.T = (int)T; p.D = D;
+    p.TBB = CPB_VITERBI_TBB;
+    p.NJ = (D > 8) ? (D - 8 + fast::B - 1) / fast::B : 0;
+    p.RB = p.NJ + p.TBB / fast::B;
+    p.mode = mode; p.out = out_bits_dev;
+    p.out_vec8 = ((L % 8) == 0 && (((uintptr_t)out_bits_dev) % 8) == 0) ? 1 : 0;
+    p.met_mask = ~fast::KeyOps<1>::FMASK;
+    p.punct_mask = mask; p.punct_len = punct_len; p.n_kept = n_kept;
+    if (fast::smem_bytes(p.RB, p.TBB, 1) > dp.smem_optin) return CPB_EUNSUPPORTED;
+    Scratch ws;
+    int rc = ws.acquire(workspace_dev, workspace_bytes, 256 + (size_t)batch * sizeof(float), st);
+    if (rc) return rc;
+    float *sc = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(ws.ptr) + 256);
+    p.frame_scale = sc;
+    const int wpb = 8;
+    // the erasures are zeros: the frame's scale is the largest magnitude among the values the depuncturing uses
+    fast::frame_scale_kernel<<<(unsigned)ceil_div(batch, wpb), wpb * 32, 0, st>>>(llr_punct_dev, n_kept, need, batch, mode, sc);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ws.release(); return record_cuda_error(e, "frame_scale_kernel", __FILE__, __LINE__); }
+    rc = launch_fast(t, p, 1, 2, st);
+    ws.release();
+    return rc;
 }
 
 }  // extern "C"

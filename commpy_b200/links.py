@@ -209,9 +209,9 @@ def _ff_taps(trellis):
     return taps
 
 
-def conv_link_tx(trellis, modem, frames, frame_bits, seed, first_frame, noise_sigma):
+def conv_link_tx(trellis, modem, frames, frame_bits, seed, first_frame, noise_sigma, puncture=None):
     """Device-side TX chain of `frames` frames starting at GLOBAL frame index `first_frame`: random message ->
-    conv_encode(..., 'cont') -> modem.modulate -> + noise_sigma * (N(0,1) + jN(0,1)).
+    conv_encode(..., 'cont') -> [puncturing(coded, puncture)] -> modem.modulate -> + noise_sigma * (N(0,1) + jN(0,1)).
 
     Returns (msg uint8 (frames, frame_bits), y complex64 (frames, frame_bits*n/bits_per_symbol)) as CUDA tensors.
     The streams depend only on (seed, global frame index): any split of the frames over calls or ranks gives the
@@ -220,17 +220,34 @@ def conv_link_tx(trellis, modem, frames, frame_bits, seed, first_frame, noise_si
     from .channelcoding.convcode import _trellis_handle
     torch = _lib.require_cuda()
     nb = int(modem.num_bits_symbol)
-    if (int(trellis.n) * int(frame_bits)) % nb:
-        raise ValueError("frame_bits * n must be a multiple of the modem's bits per symbol")
-    nsym = int(trellis.n) * int(frame_bits) // nb
+    kept = kept_bits(int(trellis.n) * int(frame_bits), puncture)
+    if kept % nb:
+        raise ValueError("the (punctured) coded bits of a frame must fill whole symbols")
+    nsym = kept // nb
     msg = torch.empty((int(frames), int(frame_bits)), dtype=torch.uint8, device="cuda")
     y = torch.empty((int(frames), nsym), dtype=torch.complex64, device="cuda")
-    rc = _lib.load().cpb_conv_link_tx(_trellis_handle(trellis), modem._handle(), C.c_int64(int(frames)),
-                                      C.c_int64(int(frame_bits)), C.c_uint64(int(seed) & ((1 << 64) - 1)),
-                                      C.c_int64(int(first_frame)), C.c_float(float(noise_sigma)), _lib.ptr(msg),
-                                      _lib.ptr(y), _lib.stream_ptr(torch))
+    if puncture is None:
+        rc = _lib.load().cpb_conv_link_tx(_trellis_handle(trellis), modem._handle(), C.c_int64(int(frames)),
+                                          C.c_int64(int(frame_bits)), C.c_uint64(int(seed) & ((1 << 64) - 1)),
+                                          C.c_int64(int(first_frame)), C.c_float(float(noise_sigma)), _lib.ptr(msg),
+                                          _lib.ptr(y), _lib.stream_ptr(torch))
+    else:
+        pv = np.ascontiguousarray(puncture, dtype=np.int32)
+        rc = _lib.load().cpb_conv_link_tx_punctured(_trellis_handle(trellis), modem._handle(), C.c_int64(int(frames)),
+                                                    C.c_int64(int(frame_bits)), C.c_uint64(int(seed) & ((1 << 64) - 1)),
+                                                    C.c_int64(int(first_frame)), C.c_float(float(noise_sigma)),
+                                                    _lib.ptr(pv), int(len(pv)), _lib.ptr(msg), _lib.ptr(y),
+                                                    _lib.stream_ptr(torch))
     _lib.check(rc, "conv_link_tx")
     return msg, y
+
+
+def kept_bits(n_coded, puncture):
+    """how many of n_coded bits puncturing(message, puncture) keeps (convcode.py:752-774)"""
+    if puncture is None:
+        return int(n_coded)
+    pv = np.asarray(puncture)
+    return int(np.sum(pv[np.arange(int(n_coded)) % len(pv)] == 1))
 
 
 class ConvLinkGPU:
@@ -240,7 +257,8 @@ class ConvLinkGPU:
     `frame_bits` information bits per frame ('cont' termination), `frames_per_batch` frames decoded per step and rank.
     """
 
-    def __init__(self, trellis, modem, frame_bits=4096, frames_per_batch=4096, decoding_type="soft", tb_depth=None, seed=0):
+    def __init__(self, trellis, modem, frame_bits=4096, frames_per_batch=4096, decoding_type="soft", tb_depth=None, seed=0,
+                 puncture=None):
         taps = _ff_taps(trellis)
         if taps is None:
             raise NotImplementedError("ConvLinkGPU generates frames on the device for k=1 feed-forward codes only")
@@ -250,9 +268,16 @@ class ConvLinkGPU:
         self.frame_bits, self.frames = int(frame_bits), int(frames_per_batch)
         self.decoding_type, self.tb_depth, self.seed = decoding_type, tb_depth, int(seed)
         nb = modem.num_bits_symbol
-        if (trellis.n * self.frame_bits) % nb:
-            raise ValueError("frame_bits * n must be a multiple of the modem's bits per symbol")
-        self.rate = Fraction(trellis.k, trellis.n)
+        # puncturing pattern over the coded stream (802.11: [1,1,1,0] = 2/3, [1,1,1,0,0,1] = 3/4, ...): punctured on the
+        # device in the TX kernel, depunctured inside the Viterbi kernel's load
+        self.puncture = None if puncture is None else [int(v) for v in puncture]
+        if self.puncture is not None and decoding_type != "soft":
+            raise ValueError("a punctured link decodes soft values")
+        n_coded = trellis.n * self.frame_bits
+        kept = kept_bits(n_coded, self.puncture)
+        if kept % nb:
+            raise ValueError("the (punctured) coded bits of a frame must fill whole symbols")
+        self.rate = Fraction(trellis.k, trellis.n) * Fraction(n_coded, kept)
 
     # -- TX chain on the device ---------------------------------------------------------------------
     def noise_std(self, snr_db):
@@ -265,7 +290,8 @@ class ConvLinkGPU:
         rank, world, _ = parallel.world()
         first = parallel.batch_first_frame(batch_index, self.frames, rank, max(world, 1))
         ns = self.noise_std(snr_db)
-        msg, y = conv_link_tx(self.trellis, self.modem, self.frames, self.frame_bits, self.seed, first, 0.5 * ns)
+        msg, y = conv_link_tx(self.trellis, self.modem, self.frames, self.frame_bits, self.seed, first, 0.5 * ns,
+                              self.puncture)
         return msg, y, ns ** 2                                                                     # links.py:329
 
     # -- RX chain: this package's kernels -------------------------------------------------------------
@@ -276,7 +302,12 @@ class ConvLinkGPU:
             rx = self.modem.demodulate_batch(y, "soft", noise_var)
         else:
             rx = self.modem.demodulate_batch(y, "hard")
-        dec = viterbi_decode_batch(rx, self.trellis, self.tb_depth, self.decoding_type)
+        if self.puncture is None:
+            dec = viterbi_decode_batch(rx, self.trellis, self.tb_depth, self.decoding_type)
+        else:
+            from .channelcoding import viterbi_decode_punctured_batch
+            dec = viterbi_decode_punctured_batch(rx, self.trellis, self.puncture, self.trellis.n * self.frame_bits,
+                                                 self.tb_depth, "soft")
         L = msg.shape[1]
         rc = _lib.load().cpb_count_errors(_lib.ptr(dec), _lib.ptr(msg), C.c_int64(msg.shape[0]), C.c_int64(L),
                                           C.c_int64(dec.shape[1]), C.c_int64(L), _lib.ptr(counters), _lib.stream_ptr(torch))

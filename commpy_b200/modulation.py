@@ -112,16 +112,29 @@ class Modem:
         _lib.check(rc, "demodulate")
         return out.reshape(tuple(y.shape[:-1]) + (y.shape[-1] * nb,)) if y.dim() > 1 else out
 
+    def demodulate_soft_host(self, input_symbols, noise_var):
+        """Soft demapper for HOST arrays through the pipelined host entry point (cpb_demod_soft_host: chunked H2D / kernel /
+        D2H on the modem handle's streams).  numpy complex array (any shape) -> float32 numpy array of LLRs, MSB first."""
+        _lib.require_cuda()
+        if not noise_var > 0:
+            raise ValueError("noise_var must be positive for soft demodulation")
+        y = np.ascontiguousarray(np.atleast_1d(input_symbols), dtype=np.complex64)
+        out = np.empty(y.size * self.num_bits_symbol, dtype=np.float32)
+        rc = _lib.load().cpb_demod_soft_host(self._handle(), _lib.ptr(y.view(np.float32)), C.c_int64(y.size),
+                                             C.c_float(noise_var), _lib.ptr(out))
+        _lib.check(rc, "demodulate")
+        return out.reshape(tuple(y.shape[:-1]) + (y.shape[-1] * self.num_bits_symbol,)) if y.ndim > 1 else out
+
     def demodulate(self, input_symbols, demod_type, noise_var=0):
         """Drop-in for Modem.demodulate (modulation.py:100-141).
 
         'hard': nearest constellation point -> its bits (int8).  'soft': exact log-sum-exp LLRs
         log(sum_{bit=1} exp(-|y-c|^2/noise_var) / sum_{bit=0} ...), float64 array, MSB first per symbol.
         Computed in float32 on the GPU (relative error ~1e-4); finite where the reference under/overflows."""
+        if demod_type == "soft":
+            return self.demodulate_soft_host(np.atleast_1d(np.asarray(input_symbols)).reshape(-1), noise_var).astype(np.float64)
         out = self.demodulate_batch(np.atleast_1d(np.asarray(input_symbols)).reshape(-1), demod_type, noise_var)
-        if demod_type == "hard":
-            return out.cpu().numpy().astype(np.int8)
-        return out.cpu().numpy().astype(np.float64)
+        return out.cpu().numpy().astype(np.int8)
 
 
 class PSKModem(Modem):

@@ -48,6 +48,24 @@ class Wifi80211:
     def _get_trellis():
         return cc.Trellis(Wifi80211.memory, Wifi80211.generator_matrix)
 
+    def link_performance_gpu(self, SNRs, send_max, err_min, send_chunk=4096, frames_per_batch=4096, seed=0, stop_early=True):
+        """The same MCS over an AWGN SISO channel, batched on the GPU(s): frames are generated, punctured, mapped and
+        disturbed on the device (cpb_conv_link_tx[_punctured]), demapped (cpb_demod_soft) and decoded with the depuncturing
+        fused into the Viterbi kernel's load (cpb_viterbi_decode_punctured).  `send_chunk` information bits per frame
+        (rounded down so that the punctured frame fills whole symbols and whole puncturing periods).  Returns the BER per
+        SNR like `ConvLinkGPU.link_performance`."""
+        num, den = self._get_coding()
+        modem = self.get_modem()
+        pattern = Wifi80211._get_puncture_matrix(num, den)
+        nb = modem.num_bits_symbol
+        unit = 1
+        while (lk.kept_bits(2 * unit, pattern) % nb) or (pattern and (2 * unit) % len(pattern)):
+            unit += 1
+        frame_bits = max(unit, (int(send_chunk) // unit) * unit)
+        self.gpu_link = lk.ConvLinkGPU(Wifi80211._get_trellis(), modem, frame_bits=frame_bits, frames_per_batch=frames_per_batch,
+                                       decoding_type="soft", seed=seed, puncture=pattern)
+        return self.gpu_link.link_performance(SNRs, send_max, err_min, stop_early=stop_early)
+
     def link_performance(self, channel, SNRs, tx_max, err_min, send_chunk=None, frame_aggregation=1, receiver=None,
                          stop_on_surpass_error=True):
         """Monte-Carlo BER of the selected MCS over `channel` (wifi80211.py:132-216): returns

@@ -92,6 +92,18 @@ int cpb_viterbi_decode_host(const cpbTrellis *t, const void *coded_host, int in_
  */
 int cpb_viterbi_decode_packed(const cpbTrellis *t, const uint8_t *coded_packed_dev, int64_t batch, int64_t n_in,
                               int tb_depth, uint8_t *out_packed_dev, void *stream);
+/*
+ * Soft / unquantized decision on PUNCTURED rows: depuncturing (convcode.py:777-804) fused into the kernel's load.
+ * llr_punct_dev: batch x n_kept float32 (what the demapper produced for the punctured stream); coded position c of the
+ * n_depunct-long mother-code stream is the next unread value when punct_vec[c % punct_len] == 1 and 0.0 otherwise;
+ * CPB_EINVAL when the row is shorter than the pattern needs (the reference raises IndexError).  punct_len <= 32.
+ * Then exactly cpb_viterbi_decode(mode) on the n_depunct values.  K = 7 fast-path trellises; CPB_EUNSUPPORTED otherwise
+ * (depuncture with commpy_b200.channelcoding.depuncturing and call cpb_viterbi_decode).
+ */
+int cpb_viterbi_punctured_workspace_bytes(int64_t batch, size_t *bytes);
+int cpb_viterbi_decode_punctured(const cpbTrellis *t, const float *llr_punct_dev, int64_t batch, int64_t n_kept,
+                                 const int32_t *punct_vec_host, int punct_len, int64_t n_depunct, int tb_depth, int mode,
+                                 uint8_t *out_bits_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
 int cpb_viterbi_decode_host_packed(const cpbTrellis *t, const uint8_t *coded_packed_host, int64_t batch,
                                    int64_t n_in, int tb_depth, uint8_t *out_packed_host);
 
@@ -101,16 +113,27 @@ int cpb_viterbi_decode_host_packed(const cpbTrellis *t, const uint8_t *coded_pac
  * L_out (batch x N) receives what the reference returns as L_ext (L_int + log(app1/app0), :145-146);
  * bits_out (nullable) receives L_out > 0 in 'decode' mode, zeros otherwise (:148-152).
  */
+int cpb_map_workspace_bytes(const cpbTrellis *t, int64_t batch, int64_t N, size_t *bytes);
 int cpb_map_decode(const cpbTrellis *t, const float *sys_dev, const float *par_dev, const float *L_int_dev,
                    int64_t batch, int64_t N, float noise_variance, int mode,
-                   float *L_out_dev, uint8_t *bits_out_dev, void *stream);
+                   float *L_out_dev, uint8_t *bits_out_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
 /*
  * perm_dev: interleaver p_array (int32, length N; interleavers.py:13-47).  L_int0_dev nullable (zeros).
  * bits_out: batch x N uint8 = deinterlv(decoder-2 hard decisions of the last iteration) (:331).
+ * workspace_dev (both functions) may be NULL (stream-ordered allocation) or >= cpb_*_workspace_bytes().
  */
+int cpb_turbo_workspace_bytes(const cpbTrellis *t, int64_t batch, int64_t N, size_t *bytes);
 int cpb_turbo_decode(const cpbTrellis *t, const float *sys_dev, const float *par1_dev, const float *par2_dev,
                      const int32_t *perm_dev, int64_t batch, int64_t N, float noise_variance, int n_iter,
-                     const float *L_int0_dev, uint8_t *bits_out_dev, void *stream);
+                     const float *L_int0_dev, uint8_t *bits_out_dev, void *workspace_dev, size_t workspace_bytes,
+                     void *stream);
+/* Host-buffer forms: chunked H2D -> kernels -> D2H pipeline on the trellis handle's internal streams; every pointer is
+ * host memory (perm_host included); L_out_host / bits_out_host nullable for cpb_map_decode_host. */
+int cpb_map_decode_host(const cpbTrellis *t, const float *sys_host, const float *par_host, const float *L_int_host,
+                        int64_t batch, int64_t N, float noise_variance, int mode, float *L_out_host, uint8_t *bits_out_host);
+int cpb_turbo_decode_host(const cpbTrellis *t, const float *sys_host, const float *par1_host, const float *par2_host,
+                          const int32_t *perm_host, int64_t batch, int64_t N, float noise_variance, int n_iter,
+                          const float *L_int0_host, uint8_t *bits_out_host);
 
 /* ---- LDPC min-sum BP: commpy/channelcoding/ldpc.py:144-254 (MSA branch :229-238, VN :243-248) ---- */
 typedef struct cpbLdpc cpbLdpc;
@@ -130,6 +153,11 @@ int cpb_ldpc_workspace_bytes(const cpbLdpc *h, int64_t batch, int precision, siz
 int cpb_ldpc_minsum(const cpbLdpc *h, void *llr_dev, int precision, int64_t batch, int n_iters,
                     uint8_t *dec_dev, void *out_llr_dev, int32_t *iters_dev,
                     void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* Host-buffer form of cpb_ldpc_minsum / cpb_ldpc_sumproduct (algorithm 0 = MSA, 1 = SPA): llr_host is clipped in
+ * place like the device form; dec_host batch x n uint8; out_llr_host / iters_host nullable. */
+int cpb_ldpc_decode_host(const cpbLdpc *h, int algorithm, void *llr_host, int precision, int64_t batch, int n_iters,
+                         uint8_t *dec_host, void *out_llr_host, int32_t *iters_host);
 
 /* Sum-product variant ('SPA', ldpc.py:209-227): same arguments and schedule; check-node rule
  * R_ij = 2 atanh(clip(prod_row tanh(Q/2) / tanh(Q_ij/2), -1, 1)), clipped to +-500.  Agrees with the reference to
@@ -151,6 +179,8 @@ int cpb_modem_is_separable(const cpbModem *m);
  */
 int cpb_demod_soft(const cpbModem *m, const float *y_dev, int64_t n_sym, float noise_var,
                    float *llr_dev, void *stream);
+/* Host-buffer form: y_host n_sym complex64, llr_host n_sym x log2(M) float32. */
+int cpb_demod_soft_host(const cpbModem *m, const float *y_host, int64_t n_sym, float noise_var, float *llr_host);
 /* bits_dev: n_sym x log2(M) uint8, nearest point (first minimum), MSB first (:121-123). */
 int cpb_demod_hard(const cpbModem *m, const float *y_dev, int64_t n_sym, uint8_t *bits_dev, void *stream);
 
@@ -171,6 +201,13 @@ int cpb_count_errors(const uint8_t *a_dev, const uint8_t *b_dev, int64_t batch, 
  */
 int cpb_conv_link_tx(const cpbTrellis *t, const cpbModem *m, int64_t frames, int64_t frame_bits, uint64_t seed,
                      int64_t first_frame, float noise_sigma, uint8_t *msg_dev, float *y_dev, void *stream);
+/* The same with puncturing (convcode.py:752-774) between the encoder and the mapper: coded bit c is kept when
+ * punct_vec[c % punct_len] == 1 (punct_len a multiple of n, <= 32); the kept bits of a frame must fill whole symbols.
+ * y_dev: frames x (kept bits / bits per symbol) complex64. */
+int cpb_conv_link_tx_punctured(const cpbTrellis *t, const cpbModem *m, int64_t frames, int64_t frame_bits,
+                               uint64_t seed, int64_t first_frame, float noise_sigma,
+                               const int32_t *punct_vec_host, int punct_len, uint8_t *msg_dev, float *y_dev,
+                               void *stream);
 
 #ifdef __cplusplus
 }

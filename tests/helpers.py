@@ -128,11 +128,14 @@ def philox4x32_10(ctr, key):
     return c.astype(np.uint32)
 
 
-def conv_link_tx_model(trellis, modem, frames, frame_bits, seed, first_frame, noise_sigma):
+def conv_link_tx_model(trellis, modem, frames, frame_bits, seed, first_frame, noise_sigma, puncture=None):
     """(msg, y) exactly as cpb_conv_link_tx defines them (float64 Box-Muller for the noise)."""
     key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    from commpy_b200.channelcoding.convcode import puncturing
     n, nb = int(trellis.n), int(modem.num_bits_symbol)
-    nsym = n * frame_bits // nb
+    ncoded = n * frame_bits
+    nkept = ncoded if puncture is None else int(np.sum(np.asarray(puncture)[np.arange(ncoded) % len(puncture)] == 1))
+    nsym = nkept // nb
     msg = np.zeros((frames, frame_bits), dtype=np.uint8)
     y = np.zeros((frames, nsym), dtype=np.complex128)
     cst = np.asarray(modem.constellation)
@@ -145,6 +148,8 @@ def conv_link_tx_model(trellis, modem, frames, frame_bits, seed, first_frame, no
         bits = ((words[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).reshape(-1)[:frame_bits]
         msg[fl] = bits
         coded = conv_encode(bits.astype(int), trellis, "cont")
+        if puncture is not None:
+            coded = puncturing(coded, puncture)
         idx = coded.reshape(-1, nb).dot(1 << np.arange(nb - 1, -1, -1))
         npair = -(-nsym // 2)
         ctr = np.zeros((npair, 4), dtype=np.uint64)

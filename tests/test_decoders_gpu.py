@@ -362,3 +362,26 @@ def test_edge_cases_other_decoders():
         for b in range(batch):
             Lo, bo = oracle.map_decode(ys[b], yp[b], tr, 0.9, La[b])
             assert np.allclose(L[b].cpu().numpy(), Lo, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("algorithm,precision", [("MSA", "fp32"), ("MSA", "fp64"), ("SPA", "fp32")])
+def test_ldpc_fer_acceptance_of_the_reference(algorithm, precision):
+    """commpy/channelcoding/tests/test_ldpc.py:28-66 on the GPU path: Gallager (96, 48) code, all-zero codeword over BPSK-AWGN,
+    100 iterations, frame error rate ~0.2 at Eb/N0 = 2.0 dB and ~0.1 at 2.5 dB (the reference's own tolerance: rtol 0.6).
+    The reference estimates each FER from 50 frame errors; here every point is 8,192 frames."""
+    import torch
+    g, params, _ = _golden_ldpc(0)                    # Gallager 96.33.964
+    n = params["n_vnodes"]
+    assert n == 96
+    rs = np.random.RandomState(321)
+    rate, Es = 0.5, 1.0
+    fer = []
+    for ebno in (2.0, 2.5):
+        noise_std = 1 / np.sqrt((10 ** (ebno / 10.0)) * rate * 2 / Es)
+        rx = 1.0 + noise_std * rs.randn(8192, n)
+        llr = 2.0 * rx / noise_std ** 2
+        dec = ldpc_bp_decode_batch(llr.astype(np.float64 if precision == "fp64" else np.float32), params, 100, precision,
+                                   return_llrs=False, decoder_algorithm=algorithm)
+        fer.append(float((dec.sum(dim=1) > 0).float().mean()))
+    np.testing.assert_allclose(fer, (0.2, 0.1), rtol=0.6, atol=0, err_msg=algorithm + " does not perform as expected")
+    assert fer[1] < fer[0]

@@ -255,3 +255,125 @@ def test_published_ber_of_reference_readme():
     from oracle import oracle
     want = oracle.viterbi_decode(hard_in[0].astype(np.float64), trellis, tb_depth, "hard")
     assert np.array_equal(dec_hard[0], want)
+
+
+@pytest.mark.gpu
+def test_counters_identical_for_1_2_4_8_ranks(monkeypatch):
+    """SURVEY 4(4) / VERDICT r1: same seed => same error counters whatever the number of ranks.  The rank layout is emulated
+    in one process (RANK / WORLD_SIZE in the environment; no process group, so the all-reduce is the sum taken here): the
+    same 1,024 global frames per step are generated and decoded as 1, 2, 4 and 8 shards."""
+    import torch
+    from commpy_b200.modulation import QAMModem
+    tr = helpers.k7()
+    snr = 11.0 + 10 * np.log10(8)
+    totals = {}
+    for world in (1, 2, 4, 8):
+        link = ConvLinkGPU(tr, QAMModem(256), frame_bits=1024, frames_per_batch=1024 // world, decoding_type="soft", seed=77)
+        tot = torch.zeros(3, dtype=torch.int64, device="cuda")
+        for rank in range(world):
+            monkeypatch.setenv("RANK", str(rank))
+            monkeypatch.setenv("WORLD_SIZE", str(world))
+            for b in range(3):
+                msg, y, nv = link.make_batch(snr, b, torch)
+                link.receive_decode_count(msg, y, nv, tot, torch)
+        totals[world] = tot.cpu().numpy().copy()
+    monkeypatch.delenv("RANK")
+    monkeypatch.delenv("WORLD_SIZE")
+    assert totals[1][0] > 0, "the test point must have bit errors to compare"
+    for world in (2, 4, 8):
+        assert np.array_equal(totals[world], totals[1]), (world, totals)
+
+
+@pytest.mark.gpu
+def test_c5_chain_256qam_soft_vs_oracle():
+    """BASELINE config 5 chain at its own shape: 256-QAM symbols of 4096-bit K=7 frames -> soft demapper -> soft Viterbi,
+    against the oracle's demapper feeding the oracle's Viterbi on the same received symbols."""
+    import torch
+    from oracle import oracle
+    from commpy_b200.modulation import QAMModem
+    tr = helpers.k7()
+    link = ConvLinkGPU(tr, QAMModem(256), frame_bits=4096, frames_per_batch=64, decoding_type="soft", seed=5)
+    bad = tot = 0
+    for ebn0 in (10.0, 13.0):
+        msg, y, nv = link.make_batch(ebn0 + 10 * np.log10(8), 0, torch)
+        cnt = torch.zeros(3, dtype=torch.int64, device="cuda")
+        dec = link.receive_decode_count(msg, y, nv, cnt, torch)[:12].cpu().numpy()
+        yy = y[:12].cpu().numpy().astype(np.complex128)
+        for f in range(12):
+            llr = oracle.demodulate(link.modem, yy[f], "soft", nv)
+            want = oracle.viterbi_decode(llr, tr, None, "soft")
+            bad += int((dec[f] != want).sum())
+            tot += want.size
+    assert bad / tot <= 1e-4, (bad, tot)
+
+
+WIFI_PATTERNS = {"2/3": [1, 1, 1, 0], "3/4": [1, 1, 1, 0, 0, 1], "5/6": [1, 1, 1, 0, 0, 1, 1, 0, 0, 1]}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rate", sorted(WIFI_PATTERNS))
+def test_punctured_viterbi_kernel_vs_oracle(rate):
+    """cpb_viterbi_decode_punctured (depuncturing fused into the kernel's load) against depuncturing() + the oracle's
+    viterbi_decode on the same punctured LLRs: both 802.11 trellises (octal K=7 and the reference's decimal-quirk one)."""
+    from oracle import oracle
+    from commpy_b200.channelcoding import depuncturing, puncturing, viterbi_decode_punctured_batch
+    pv = WIFI_PATTERNS[rate]
+    rs = np.random.RandomState(41)
+    for tr in (helpers.k7(), helpers.k7_wifi_quirk()):
+        for nbits in (600, 1020):
+            msgs = rs.randint(0, 2, (40, nbits))
+            coded = helpers.encode_batch(msgs, tr, "cont")
+            y = (2.0 * coded - 1) + 0.45 * rs.randn(*coded.shape)
+            llr = 2 * y / 0.45 ** 2
+            rows = np.stack([puncturing(r, pv) for r in llr])
+            got = viterbi_decode_punctured_batch(rows.astype(np.float32), tr, pv, coded.shape[1]).cpu().numpy()
+            dep = np.stack([depuncturing(r, pv, coded.shape[1]) for r in rows])
+            want = oracle.viterbi_decode_batch(dep, tr, None, "soft", threads=4)
+            assert (got != want).mean() <= 2e-4, (rate, nbits, (got != want).sum())
+            assert abs(int((got != msgs).sum()) - int((want != msgs).sum())) <= 10
+    with pytest.raises(IndexError):
+        viterbi_decode_punctured_batch(rows[:, :-5].astype(np.float32), tr, pv, coded.shape[1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("modem_m,rate,frame_bits", [(4, "3/4", 1536), (256, "3/4", 1536), (256, "5/6", 1600), (64, "2/3", 1536)])
+def test_conv_link_tx_punctured_matches_numpy_model(modem_m, rate, frame_bits):
+    """The TX kernel with puncturing between encoder and mapper: message bits and noiseless symbols equal the NumPy model
+    (Philox message, conv_encode, puncturing, modulate), whatever the split into calls."""
+    import torch
+    from commpy_b200.links import conv_link_tx
+    from commpy_b200.modulation import QAMModem
+    tr = helpers.k7_wifi_quirk()
+    modem = QAMModem(modem_m)
+    pv = WIFI_PATTERNS[rate]
+    msg, y = conv_link_tx(tr, modem, 6, frame_bits, seed=123456789, first_frame=10, noise_sigma=0.0, puncture=pv)
+    m_ref, y_ref = helpers.conv_link_tx_model(tr, modem, 6, frame_bits, 123456789, 10, 0.0, puncture=pv)
+    assert np.array_equal(msg.cpu().numpy(), m_ref)
+    assert np.allclose(y.cpu().numpy(), y_ref, atol=1e-5)
+    msg2, y2 = conv_link_tx(tr, modem, 2, frame_bits, seed=123456789, first_frame=13, noise_sigma=0.7, puncture=pv)
+    msg3, y3 = conv_link_tx(tr, modem, 6, frame_bits, seed=123456789, first_frame=10, noise_sigma=0.7, puncture=pv)
+    assert torch.equal(msg2, msg3[3:5]) and torch.equal(y2, y3[3:5])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mcs", [2, 8, 9])
+def test_wifi80211_gpu_link_ber_matches_reference_golden(mcs):
+    """the batched punctured GPU link (Wifi80211.link_performance_gpu) against BERs measured with the
+    UNMODIFIED reference's Wifi80211.link_performance (oracle/make_wifi_golden.py -> tests/golden/wifi_ber.npz): same MCS,
+    same trellis quirk, same SNR definition; the reference points have a few hundred bit errors (bursty), so the
+    comparison allows 40 % plus three binomial sigmas."""
+    import os
+    from commpy_b200.wifi80211 import Wifi80211
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wifi_ber.npz"))
+    snrs, fe, chunk = g["mcs%d_snr" % mcs], g["mcs%d_frame_errors" % mcs].astype(np.float64), int(g["chunk"])
+    ref = fe.mean(axis=1) / chunk                                   # BER of the reference at each point
+    se = fe.std(axis=1, ddof=1) / chunk / np.sqrt(fe.shape[1])      # its standard error (frames fail as a whole: bursty)
+    w = Wifi80211(mcs)
+    got = []
+    for snr in snrs:                                                # frames of the reference's length: the quirk code propagates errors
+        got.append(w.link_performance_gpu([float(snr)], send_max=6e6, err_min=10 ** 9, send_chunk=chunk, frames_per_batch=2048,
+                                          seed=3, stop_early=False)[0])
+    assert w.gpu_link.frame_bits == chunk
+    for b_ref, s_ref, b_gpu in zip(ref, se, got):
+        assert abs(b_gpu - b_ref) <= 4 * s_ref + 0.15 * b_ref + 2e-3, (mcs, list(snrs), list(ref), list(se), got)
+    assert max(ref) > 0.01, "the golden points must sit inside the waterfall"
