@@ -468,8 +468,8 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
         // component o = Hamming distance to output symbol o (convcode.py:579) in the metric field, frame B in the high half
         if (tid < 16) {
             // table index: r0A | r1A<<1 | r0B<<2 | r1B<<3 (byte input) or symA | symB<<2 with sym = r0<<1 | r1 (packed input)
-            const int a = IOP ? (tid & 3) : (((tid & 1) << 1) | ((tid >> 1) & 1));
-            const int b = IOP ? (tid >> 2) : ((((tid >> 2) & 1) << 1) | ((tid >> 3) & 1));
+            const int a = (IOP == 1) ? (tid & 3) : (((tid & 1) << 1) | ((tid >> 1) & 1));
+            const int b = (IOP == 1) ? (tid >> 2) : ((((tid >> 2) & 1) << 1) | ((tid >> 3) & 1));
             uint32_t e[4];
             for (int o = 0; o < 4; ++o) e[o] = ((uint32_t)__popc(o ^ a) << FB) | ((uint32_t)__popc(o ^ b) << (16 + FB));
             sm_at<uint4>(sm.lut + tid * 16) = make_uint4(e[0], e[1], e[2], e[3]);
@@ -486,7 +486,7 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
     for (int fi = 0; fi < PACK; ++fi) {
         fr[fi] = base + (int64_t)fi * BD + tid;
         if (fr[fi] < p.batch) valid_mask |= 1 << fi; else fr[fi] = p.batch - 1;
-        outp[fi] = p.out + fr[fi] * (int64_t)(IOP ? (p.L >> 3) : p.L);
+        outp[fi] = p.out + fr[fi] * (int64_t)(IOP == 1 ? (p.L >> 3) : p.L);
     }
 
     // float input: the frame's own power-of-two scale (frame_scale_kernel), so a frame decodes identically
@@ -524,7 +524,7 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
         if (PACK == 2) {
             // a = the 4 coded bytes of frame A, b = frame B; past the data: zeros (convcode.py:727-728)
             uint32_t a = 0u, b = 0u;
-            if (IOP) {
+            if (IOP == 1) {
                 // bit-packed input: the byte that holds the pair (2 pairs of steps per byte, first element in bit 7)
                 if (pr < npairs_in) {
                     a = __ldg(c8 + fr[0] * (p.n_in >> 3) + (pr >> 1));
@@ -584,13 +584,13 @@ __device__ __forceinline__ void viterbi_fast_body(const Params &p)
     // Byte (w >> 24) = table index of step a | table index of step b << 4.
     auto gather = [&](const Raw &r) {
         Raw g = r;
-        if (PACK == 2 && !IOP) g.w[0] = (r.w[0] & 0x01010101u) * 0x01021020u + (r.w[1] & 0x01010101u) * 0x04084080u;
+        if (PACK == 2 && IOP != 1) g.w[0] = (r.w[0] & 0x01010101u) * 0x01021020u + (r.w[1] & 0x01010101u) * 0x04084080u;
         return g;
     };
     // the four branch metrics (in the metric field) of step h (0 / 1) of a (gathered) pair
     // (bit-packed input: `odd` says whether the pair is the second one of its byte)
     auto make_bm = [&](const Raw &r, int h, uint32_t (&Bm)[4], int odd = 0) {
-        if (PACK == 2 && IOP) {
+        if (PACK == 2 && IOP == 1) {
             // received symbol of frame A = bits (7,6) >> 2*(2*odd + h) of its byte, same for frame B; table index = A | B << 2
             const int sh = 2 * (2 * odd + h);
             const uint32_t off = (((r.w[0] << sh) >> 2) & 0x30u) | ((r.w[1] << sh) & 0xC0u);
