@@ -369,3 +369,74 @@ class ConvLinkGPU:
         if return_counters:
             return BERs, grand
         return BERs
+
+
+def turbo_link_tx(trellis, interleaver, frames, frame_bits, seed, first_frame, noise_sigma):
+    """Device-side TX chain of a turbo-coded BPSK link (cpb_turbo_link_tx): random message -> turbo_encode(msg, trellis,
+    trellis, interleaver) -> 2x-1 -> + noise_sigma * N(0,1), for `frames` frames starting at GLOBAL frame `first_frame`.
+
+    Returns (msg uint8, sys, par1, par2 float32), each (frames, frame_bits), CUDA tensors: what map_decode / turbo_decode
+    take.  The streams depend only on (seed, global frame index)."""
+    import ctypes as C
+    from .channelcoding.convcode import _trellis_handle
+    from .channelcoding.turbo import _checked_perm
+    torch = _lib.require_cuda()
+    N = int(frame_bits)
+    perm = torch.from_numpy(_checked_perm(interleaver, N)).cuda()
+    msg = torch.empty((int(frames), N), dtype=torch.uint8, device="cuda")
+    ys, y1, y2 = (torch.empty((int(frames), N), dtype=torch.float32, device="cuda") for _ in range(3))
+    rc = _lib.load().cpb_turbo_link_tx(_trellis_handle(trellis), _lib.ptr(perm), C.c_int64(int(frames)), C.c_int64(N),
+                                       C.c_uint64(int(seed) & ((1 << 64) - 1)), C.c_int64(int(first_frame)),
+                                       C.c_float(float(noise_sigma)), _lib.ptr(msg), _lib.ptr(ys), _lib.ptr(y1), _lib.ptr(y2),
+                                       _lib.stream_ptr(torch))
+    _lib.check(rc, "turbo_link_tx")
+    return msg, ys, y1, y2
+
+
+class TurboLinkGPU:
+    """Batched rate-1/3 turbo link over BPSK-AWGN on the GPU(s): frames generated (cpb_turbo_link_tx), decoded
+    (cpb_turbo_decode) and counted (cpb_count_errors) on the device; the error counters are the only thing all-reduced."""
+
+    def __init__(self, trellis, interleaver, frame_bits, frames_per_batch=1024, iterations=6, seed=0):
+        self.trellis, self.interleaver = trellis, interleaver
+        self.frame_bits, self.frames, self.iterations, self.seed = int(frame_bits), int(frames_per_batch), int(iterations), int(seed)
+
+    def noise_variance(self, ebn0_db):
+        return 1.0 / (2.0 * (1.0 / 3.0) * 10 ** (ebn0_db / 10.0))
+
+    def make_batch(self, ebn0_db, batch_index):
+        rank, world, _ = parallel.world()
+        first = parallel.batch_first_frame(batch_index, self.frames, rank, max(world, 1))
+        s2 = self.noise_variance(ebn0_db)
+        return turbo_link_tx(self.trellis, self.interleaver, self.frames, self.frame_bits, self.seed, first, math.sqrt(s2)) + (s2,)
+
+    def decode_count(self, msg, ys, y1, y2, s2, counters, torch):
+        import ctypes as C
+        from .channelcoding import turbo_decode_batch
+        dec = turbo_decode_batch(ys, y1, y2, self.trellis, s2, self.iterations, self.interleaver)
+        L = msg.shape[1]
+        rc = _lib.load().cpb_count_errors(_lib.ptr(dec), _lib.ptr(msg), C.c_int64(msg.shape[0]), C.c_int64(L), C.c_int64(L),
+                                          C.c_int64(L), _lib.ptr(counters), _lib.stream_ptr(torch))
+        _lib.check(rc, "count_errors")
+        return dec
+
+    def link_performance(self, EbN0s, send_max, err_min):
+        """BER per Eb/N0 (dB): a point ends when the global counters reach `err_min` bit errors or `send_max` bits."""
+        torch = _lib.require_cuda()
+        BERs = np.zeros(len(EbN0s))
+        batch_index = 0
+        for i, e in enumerate(EbN0s):
+            tot = torch.zeros(3, dtype=torch.int64, device="cuda")
+            while True:
+                msg, ys, y1, y2, s2 = self.make_batch(float(e), batch_index)
+                batch_index += 1
+                local = torch.zeros(3, dtype=torch.int64, device="cuda")
+                self.decode_count(msg, ys, y1, y2, s2, local, torch)
+                local[2] = msg.numel()
+                parallel.allreduce_counters(local)
+                tot += local
+                c = tot.cpu().numpy()
+                if not parallel.stop_rule(c, send_max, err_min):
+                    break
+            BERs[i] = c[0] / c[2]
+        return BERs

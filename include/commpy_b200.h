@@ -209,6 +209,18 @@ int cpb_conv_link_tx_punctured(const cpbTrellis *t, const cpbModem *m, int64_t f
                                const int32_t *punct_vec_host, int punct_len, uint8_t *msg_dev, float *y_dev,
                                void *stream);
 
+/* ---- transmit side of a turbo-coded BPSK-AWGN link: commpy/channelcoding/turbo.py:14-59 (turbo_encode) + mapper + AWGN ---- */
+/*
+ * Rate-1/2 systematic trellis (k = 1, n = 2, MSB of the output symbol = input; <= 32 states), the same for both component
+ * encoders like turbo_decode assumes.  Per frame: msg (Philox bits), sys = msg, par1 = parity over msg, par2 = parity over
+ * msg[perm] -- the streams turbo_encode returns (its zero-bit 'rsc' tails are cut off again, :55-57: unterminated
+ * encoders started in state 0) -- each mapped to 2x-1 and disturbed by noise_sigma * N(0,1).
+ * msg_dev: frames x N uint8; sys / par1 / par2: frames x N float32.  Counter-based randomness keyed by (seed, global frame).
+ */
+int cpb_turbo_link_tx(const cpbTrellis *t, const int32_t *perm_dev, int64_t frames, int64_t N, uint64_t seed,
+                      int64_t first_frame, float noise_sigma, uint8_t *msg_dev, float *sys_dev, float *par1_dev,
+                      float *par2_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

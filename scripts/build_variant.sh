@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/.."
 tag=$1; shift
 mkdir -p build/variants/$tag
-for f in common viterbi bcjr ldpc demap count pipeline hostapi txlink turbo_fused; do
+for f in common viterbi bcjr ldpc demap count pipeline hostapi txlink turbolink; do
   [ -f commpy_b200/csrc/$f.cu ] || continue
   if [ "$f" = "viterbi" ] || [ ! -f build/$f.o ] || [ -n "$VARIANT_ALL" ]; then
     /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --fmad=true -DCPB_BUILDING=1 "$@" -c commpy_b200/csrc/$f.cu -o build/variants/$tag/$f.o &

@@ -162,3 +162,34 @@ def conv_link_tx_model(trellis, modem, frames, frame_bits, seed, first_frame, no
         z = np.stack([za, zb], axis=1).reshape(-1)[:nsym]
         y[fl] = cst[idx] + noise_sigma * z
     return msg, y
+
+
+def turbo_link_tx_model(trellis, interleaver, frames, frame_bits, seed, first_frame, noise_sigma):
+    """(msg, sys, par1, par2) exactly as cpb_turbo_link_tx defines them: Philox message bits, the host turbo_encode mirror
+    (commpy/channelcoding/turbo.py:14-59), BPSK 2x-1, float64 Box-Muller noise (stream j uses Philox counter word 2 + j)."""
+    from commpy_b200.channelcoding import turbo_encode
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    N = frame_bits
+    msg = np.zeros((frames, N), dtype=np.uint8)
+    ys = np.zeros((frames, 3, N))
+    for fl in range(frames):
+        f = first_frame + fl
+        nblk = -(-N // 128)
+        ctr = np.zeros((nblk, 4), dtype=np.uint64)
+        ctr[:, 0], ctr[:, 1], ctr[:, 2], ctr[:, 3] = f & 0xFFFFFFFF, f >> 32, np.arange(nblk), 0
+        words = philox4x32_10(ctr, key).reshape(-1)
+        bits = ((words[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).reshape(-1)[:N]
+        msg[fl] = bits
+        streams = turbo_encode(bits.astype(int), trellis, trellis, interleaver)
+        nq = -(-N // 4)
+        for j in range(3):
+            ctr = np.zeros((nq, 4), dtype=np.uint64)
+            ctr[:, 0], ctr[:, 1], ctr[:, 2], ctr[:, 3] = f & 0xFFFFFFFF, f >> 32, np.arange(nq), 2 + j
+            r = philox4x32_10(ctr, key).astype(np.float64)
+            u1a, u2a = r[:, 0] * 2.0 ** -32 + 2.0 ** -33, r[:, 1] * 2.0 ** -32
+            u1b, u2b = r[:, 2] * 2.0 ** -32 + 2.0 ** -33, r[:, 3] * 2.0 ** -32
+            za = np.sqrt(-2 * np.log(u1a)) * np.exp(2j * np.pi * u2a)
+            zb = np.sqrt(-2 * np.log(u1b)) * np.exp(2j * np.pi * u2b)
+            z = np.stack([za.real, za.imag, zb.real, zb.imag], axis=1).reshape(-1)[:N]
+            ys[fl, j] = (2.0 * np.asarray(streams[j][:N], dtype=np.float64) - 1.0) + noise_sigma * z
+    return msg, ys[:, 0], ys[:, 1], ys[:, 2]

@@ -377,3 +377,31 @@ def test_wifi80211_gpu_link_ber_matches_reference_golden(mcs):
     for b_ref, s_ref, b_gpu in zip(ref, se, got):
         assert abs(b_gpu - b_ref) <= 4 * s_ref + 0.15 * b_ref + 2e-3, (mcs, list(snrs), list(ref), list(se), got)
     assert max(ref) > 0.01, "the golden points must sit inside the waterfall"
+
+
+@pytest.mark.gpu
+def test_turbo_link_tx_kernel_matches_numpy_model_and_link_runs():
+    """cpb_turbo_link_tx (device-side turbo_encode + BPSK + AWGN): message bits and the noiseless streams
+    equal the host turbo_encode mirror on the Philox message (incl. its unterminated-'rsc' accident), the noise matches the
+    float64 Box-Muller model, frames do not depend on the split into calls; the batched turbo link's BER falls with Eb/N0."""
+    import torch
+    from commpy_b200.channelcoding import RandInterlv
+    from commpy_b200.links import TurboLinkGPU, turbo_link_tx
+    rsc = helpers.rsc_k4()
+    for N in (256, 1000):
+        il = RandInterlv(N, 1)
+        want = helpers.turbo_link_tx_model(rsc, il, 4, N, 99, (1 << 32) + 3, 0.0)
+        got = turbo_link_tx(rsc, il, 4, N, 99, (1 << 32) + 3, 0.0)
+        assert np.array_equal(got[0].cpu().numpy(), want[0])
+        for a, b in zip(got[1:], want[1:]):
+            assert np.array_equal(a.cpu().numpy(), b.astype(np.float32))
+        wn = helpers.turbo_link_tx_model(rsc, il, 4, N, 99, (1 << 32) + 3, 0.8)
+        gn = turbo_link_tx(rsc, il, 4, N, 99, (1 << 32) + 3, 0.8)
+        for a, b in zip(gn[1:], wn[1:]):
+            assert np.abs(a.cpu().numpy() - b).max() < 2e-3
+        part = turbo_link_tx(rsc, il, 2, N, 99, (1 << 32) + 5, 0.8)
+        for a, b in zip(part, gn):
+            assert torch.equal(a, b[2:])
+    link = TurboLinkGPU(rsc, RandInterlv(1024, 1), 1024, frames_per_batch=256, iterations=4, seed=8)
+    bers = link.link_performance([0.0, 1.5], send_max=1e6, err_min=10 ** 9)
+    assert bers[0] > 5 * bers[1] and bers[0] > 1e-3, bers
