@@ -89,7 +89,7 @@ def test_batch_first_frame_tiles_the_frame_axis(monkeypatch):
     from commpy_b200.modulation import QAMModem
     import helpers
     calls = []
-    monkeypatch.setattr(links, "conv_link_tx", lambda tr, modem, frames, bits, seed, first, sigma: (calls.append((frames, bits, seed, first)) or (None, None)))
+    monkeypatch.setattr(links, "conv_link_tx", lambda tr, modem, frames, bits, seed, first, sigma, puncture=None: (calls.append((frames, bits, seed, first)) or (None, None)))
     monkeypatch.setenv("RANK", "3"); monkeypatch.setenv("WORLD_SIZE", "4")
     link = links.ConvLinkGPU(helpers.k7(), QAMModem(4), frame_bits=64, frames_per_batch=10, seed=9)
     link.make_batch(6.0, 5)
