@@ -17,7 +17,8 @@ Workloads (BASELINE.json configs; the default is the headline metric's):
 A "step" is one pass of the hot path over one batch of synthetic frames already resident in HBM (sized so that the
 timed region of 20 steps is >= 100 ms): decode kernels + error count, the error counters accumulate on the device and
 their all-reduce (the only collective) is issued asynchronously once per step.  Frames shard across ranks with no
-data-path collective (weak scaling, except turbo_c3 whose 8,192 codewords are split: strong).  `e2e` times the same
+data-path collective (weak scaling, except turbo_c3 and link_c5 whose fixed totals -- 8,192 codewords, 1e8 symbols per
+point -- are split: strong).  `e2e` times the same
 work through the public host-buffer API (pinned host memory, H2D and D2H inside the timed region).
 `--impl reference` times the CPU restatement of the reference's algorithm (oracle/, fp64, all host threads) on the same
 workload -- the Python reference itself cannot travel to the GPU box (~1.5 codewords/s/core).
@@ -539,6 +540,7 @@ class LinkWorkload(Workload):
     link_performance over a 5-point Eb/N0 sweep, ~1e8 symbols per point over all ranks; one step = the whole sweep."""
     metric = "symbols/sec (256-QAM soft demap + K=7 soft Viterbi link_performance sweep)"
     unit = "symbols/s"
+    scaling = "strong"
     ncounters = 3
 
     def __init__(self):
@@ -553,7 +555,7 @@ class LinkWorkload(Workload):
     def describe(self):
         return {"workload": self.name, "modem": "QAMModem(256), Es=170", "code": "K=7 (0o133,0o171) rate 1/2, 'cont', 4096-bit frames",
                 "decoding_type": "soft", "tb_depth": 30, "ebn0_db": self.ebn0, "symbols_per_point_all_gpus": self.frames_point * 1024,
-                "frames_per_batch_per_gpu": "frames_per_point / (2 * n_gpus)", "alg_bytes_per_symbol": self.alg_bytes,
+                "frames_per_batch_per_gpu": "frames_per_point / n_gpus (one batch per point)", "alg_bytes_per_symbol": self.alg_bytes,
                 "l2": "one batch of symbols + LLRs is > 1 GB per GPU at N=1"}
 
     def units_per_step(self, world):
@@ -564,7 +566,7 @@ class LinkWorkload(Workload):
         from commpy_b200.links import ConvLinkGPU
         from commpy_b200.modulation import QAMModem
         self.world = world
-        fpb = self.frames_point // (2 * world)
+        fpb = self.frames_point // world
         self.link = ConvLinkGPU(helpers.k7(), QAMModem(256), frame_bits=self.frame_bits, frames_per_batch=fpb, decoding_type="soft", seed=4)
         self.snrs = [e + 10 * math.log10(8) for e in self.ebn0]
         self.kernel_launches_per_step = len(self.ebn0) * 2 * 5 + len(self.ebn0) * 5

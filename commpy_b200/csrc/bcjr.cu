@@ -2,18 +2,25 @@
 // (_backward_recursion), :114-158 (_forward_recursion_decoding), :163-251 (map_decode) and the iteration
 // loop of :254-333 (turbo_decode).
 //
-// The reference works with probabilities renormalised every step; that is the exact log-MAP algorithm, so the
-// kernels run it in the log domain with the exact max* (max + log1p(exp(-|a-b|))):
+// Kernel families (all compute the exact log-MAP of the reference, float32 instead of float64):
+//   tpf::map_lin_kernel<T>   the hot one (aligned frames, compile-time trellis T): PROBABILITY domain like the reference
+//                            itself (renormalised every step, turbo.py:106-111,155), branch weights relative to the
+//                            step's best symbol (all <= 1: nothing underflows), one THREAD per (frame, window of 1024
+//                            steps) with a 96-step warm-up of alpha and beta over the neighbouring windows, beta
+//                            checkpointed every 8 steps in a global scratch and recomputed per segment in shared memory;
+//                            in the turbo loop it writes the extrinsic L - L_int itself.
+//   tpf::map_ckpt_kernel /   log2-domain exact max* forms of the same thread mapping (unaligned lengths; compile-time
+//   tpf::map_tpf_kernel      switch CPB_BCJR_LOGDOMAIN).
+//   map_kernel<S>            table-driven fallback for any other rate-1/2 trellis with <= 32 states: one LANE per state,
+//                            32/S frames per warp, neighbour metrics by warp shuffle, full-frame recursions (no windows),
+//                            log domain:
 //   gamma_t(s,u) = -((ys_t-(2cs-1))^2 + (yp_t-(2cp-1))^2) / (2 sigma^2)         turbo.py:62-76   (cs = MSB of the
 //                                                                                output symbol, cp = LSB, :97-99)
 //   beta_{t-1}(s) = max*_u  beta_t(ns(s,u)) + gamma_t(s,u) + u*La_t             :106-108, beta_N = 0 (:225-226)
 //   alpha_t(ns)   = max*    alpha_{t-1}(s)  + gamma_t(s,u) + u*La_t             :136-138, alpha_0 = delta(s,0)
 //   L_t = La_t + max*_s[alpha_{t-1}(s)+gamma_t(s,1)+beta_t(ns(s,1))] - max*_s[... u = 0 ...]     :141-146
 // (log P(u) = u*La - softplus(La); the common term cancels like the reference's normalisations do).
-// Thread mapping: one LANE PER STATE, 32/S frames per warp; neighbour metrics move by warp shuffle, received
-// values are loaded S steps at a time (one coalesced 4*S-byte segment per frame) and broadcast by shuffle,
-// beta is parked in a global scratch [frame][t][state].  No windowing: the recursions span the whole frame
-// exactly like the reference.
+// The turbo loop (cpb_turbo_decode) is 2 MAP launches + 2 row-staged interleaver launches per iteration.
 #include <algorithm>
 
 #include <cstdlib>

@@ -35,7 +35,7 @@ int cpb_map_decode_host(const cpbTrellis *t, const float *sys_host, const float 
     // L_out is always needed by the kernel: give it a scratch segment when it is not returned
     std::vector<HostSeg> ins = {{sys_host, nullptr, row}, {par_host, nullptr, row}, {L_int_host, nullptr, row}};
     if (!want_L) ins.push_back({sys_host, nullptr, row});         // an extra input-sized slot used as the L_out scratch
-    return pipe_run(const_cast<cpbTrellis *>(t)->pipe, ins, copy_outs, batch, pipe_chunk(batch, 256, 32),
+    return pipe_run(const_cast<cpbTrellis *>(t)->pipe, ins, copy_outs, batch, pipe_chunk(batch, 2048, 32),
                     [&](const std::vector<void *> &din, const std::vector<void *> &dout, int64_t, int64_t nb, cudaStream_t st) {
                         float *L = want_L ? static_cast<float *>(dout[0]) : static_cast<float *>(din[3]);
                         uint8_t *b = want_b ? static_cast<uint8_t *>(dout[want_L ? 1 : 0]) : nullptr;
@@ -57,8 +57,9 @@ int cpb_turbo_decode_host(const cpbTrellis *t, const float *sys_host, const floa
     if (e != cudaSuccess) { cudaFree(perm_dev); return record_cuda_error(e, "perm upload", __FILE__, __LINE__); }
     std::vector<HostSeg> ins = {{sys_host, nullptr, row}, {par1_host, nullptr, row}, {par2_host, nullptr, row}};
     if (L_int0_host) ins.push_back({L_int0_host, nullptr, row});
+    // (a chunk must still fill the GPU: 2,048 codewords x 6 windows are 384 warps)
     const int rc = pipe_run(const_cast<cpbTrellis *>(t)->pipe, ins, {{nullptr, bits_out_host, (size_t)N}}, batch,
-                            pipe_chunk(batch, 256, 32),
+                            pipe_chunk(batch, 2048, 32),
                             [&](const std::vector<void *> &din, const std::vector<void *> &dout, int64_t, int64_t nb, cudaStream_t st) {
                                 return cpb_turbo_decode(t, static_cast<const float *>(din[0]), static_cast<const float *>(din[1]),
                                                         static_cast<const float *>(din[2]), perm_dev, nb, N, noise_variance, n_iter,
@@ -80,24 +81,22 @@ int cpb_ldpc_decode_host(const cpbLdpc *h, int algorithm, void *llr_host, int pr
     cpb_ldpc_dims(h, &m, &n);
     const size_t esz = (precision == CPB_LDPC_FP64) ? 8 : 4;
     const size_t row = (size_t)n * esz;
-    // the reference clips the caller's array in place (ldpc.py:186)
-    if (precision == CPB_LDPC_FP64) {
-        double *x = static_cast<double *>(llr_host);
-        for (int64_t i = 0; i < batch * (int64_t)n; ++i) x[i] = std::min(500.0, std::max(-500.0, x[i]));
-    } else {
-        float *x = static_cast<float *>(llr_host);
-        for (int64_t i = 0; i < batch * (int64_t)n; ++i) x[i] = std::min(500.0f, std::max(-500.0f, x[i]));
-    }
     std::vector<HostSeg> outs = {{nullptr, dec_host, (size_t)n}};
     if (out_llr_host) outs.push_back({nullptr, out_llr_host, row});
     if (iters_host) outs.push_back({nullptr, iters_host, sizeof(int32_t)});
     return pipe_run(cpb_ldpc_pipe(const_cast<cpbLdpc *>(h)), {{llr_host, nullptr, row}}, outs, batch, pipe_chunk(batch, 128, 128),
-                    [&](const std::vector<void *> &din, const std::vector<void *> &dout, int64_t, int64_t nb, cudaStream_t st) {
+                    [&](const std::vector<void *> &din, const std::vector<void *> &dout, int64_t f0, int64_t nb, cudaStream_t st) {
                         void *ol = out_llr_host ? dout[1] : nullptr;
                         int32_t *it = iters_host ? static_cast<int32_t *>(dout[out_llr_host ? 2 : 1]) : nullptr;
-                        if (algorithm == 0)
-                            return cpb_ldpc_minsum(h, din[0], precision, nb, n_iters, static_cast<uint8_t *>(dout[0]), ol, it, nullptr, 0, st);
-                        return cpb_ldpc_sumproduct(h, din[0], precision, nb, n_iters, static_cast<uint8_t *>(dout[0]), ol, it, nullptr, 0, st);
+                        int rc = (algorithm == 0)
+                            ? cpb_ldpc_minsum(h, din[0], precision, nb, n_iters, static_cast<uint8_t *>(dout[0]), ol, it, nullptr, 0, st)
+                            : cpb_ldpc_sumproduct(h, din[0], precision, nb, n_iters, static_cast<uint8_t *>(dout[0]), ol, it, nullptr, 0, st);
+                        if (rc) return rc;
+                        // the reference clips the caller's array in place (ldpc.py:186): the kernel clipped its device copy,
+                        // which goes back over the caller's rows
+                        cudaError_t e = cudaMemcpyAsync(static_cast<char *>(llr_host) + (size_t)f0 * row, din[0], (size_t)nb * row,
+                                                        cudaMemcpyDeviceToHost, st);
+                        return e == cudaSuccess ? CPB_OK : record_cuda_error(e, "D2H (clipped llr)", __FILE__, __LINE__);
                     });
 }
 

@@ -11,7 +11,7 @@ gi, bi = hdr.index("Grid Size"), hdr.index("Block Size")
 agg = OrderedDict()
 for r in rows[1:]:
     name = r[ki]
-    ours = any(t in name for t in ("fast::", "gen::", "count::", "tpf::", "bcjr::", "ldpc::", "bulk::", "demap::", "txlink::"))
+    ours = any(t in name for t in ("fast::", "gen::", "count::", "tpf::", "bcjr::", "ldpc::", "bulk::", "demap::", "txlink::", "turbolink::", "count_errors"))
     key = (name if ours else "(torch data-generation / copy kernels, outside the timed region)", r[gi], r[bi])
     a = agg.setdefault(key, [0, 0.0])
     a[0] += 1
