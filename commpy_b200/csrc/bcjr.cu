@@ -769,10 +769,10 @@ static int launch(const Params &p, bool vec, cudaStream_t st)
         grid = (unsigned)ceil_div(p.NT, bd);
         const size_t smem = sizeof(float) * CK * (T::S + 3) * bd;
 #ifdef CPB_BCJR_LOGDOMAIN
-        CPB_CUDA(cudaFuncSetAttribute(map_ckpt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { const int rc_ = ensure_dyn_smem(reinterpret_cast<const void *>(map_ckpt_kernel<T>), smem); if (rc_) return rc_; }
         map_ckpt_kernel<T><<<grid, bd, smem, st>>>(p);
 #else
-        CPB_CUDA(cudaFuncSetAttribute(map_lin_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { const int rc_ = ensure_dyn_smem(reinterpret_cast<const void *>(map_lin_kernel<T>), smem); if (rc_) return rc_; }
         map_lin_kernel<T><<<grid, bd, smem, st>>>(p);
 #endif
     } else if (vec) map_tpf_kernel<T, 4><<<grid, 128, 0, st>>>(p);
@@ -1048,16 +1048,10 @@ int cpb_turbo_decode(const cpbTrellis *t, const float *sys_dev, const float *par
         const bool rows = (size_t)N * sizeof(float) <= 96 * 1024;
         const size_t rsm = (size_t)N * sizeof(float);
         if (rows) {
-            static thread_local size_t opted[64] = {0};          // per device: largest row already opted in
-            int dev = 0;
-            cudaGetDevice(&dev);
-            if (dev < 0 || dev >= 64) dev = 0;
-            if (opted[dev] < rsm) {
-                cudaFuncSetAttribute(bcjr::row_gather_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
-                cudaFuncSetAttribute(bcjr::row_scatter_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
-                cudaFuncSetAttribute(bcjr::row_scatter_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)N);
-                opted[dev] = rsm;
-            }
+            rc = ensure_dyn_smem(reinterpret_cast<const void *>(bcjr::row_gather_sub_kernel), rsm);
+            if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void *>(bcjr::row_scatter_sub_kernel), rsm);
+            if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void *>(bcjr::row_scatter_bits_kernel), (size_t)N);
+            if (rc) break;
         }
         if (rows) bcjr::row_gather_sub_kernel<<<(unsigned)nb, 256, rsm, st>>>(sy, nullptr, perm_dev, (int)N, sys_i);
         else bcjr::gather_sub_kernel<<<eg, 256, 0, st>>>(sy, nullptr, perm_dev, nb, (int)N, sys_i);          // :310

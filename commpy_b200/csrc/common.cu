@@ -1,5 +1,7 @@
 // Status strings, device properties, scratch allocation (host-side plumbing of libcommpy_b200.so).
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -49,6 +51,21 @@ const DeviceProps &device_props()
         have[dev] = true;
     }
     return cache[dev];
+}
+
+int ensure_dyn_smem(const void *kernel, size_t bytes)
+{
+    static std::mutex mu;
+    static std::unordered_map<unsigned long long, size_t> done;      // (kernel, device) -> largest size opted in
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long key = (unsigned long long)(uintptr_t)kernel * 131ull + (unsigned long long)dev;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= bytes) return CPB_OK;
+    CPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    done[key] = bytes;
+    return CPB_OK;
 }
 
 int Scratch::acquire(void *user, size_t user_bytes, size_t need, cudaStream_t s)

@@ -38,6 +38,9 @@ struct Scratch {
     void release();
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize opt-in, made once per (kernel, device) and size: launches do not pay for it
+int ensure_dyn_smem(const void *kernel, size_t bytes);
+
 // explicit test / experiment switches (cpb_set_option); read with relaxed atomics, never from the environment
 int option(int id);
 

@@ -646,8 +646,7 @@ static int run(const cpbLdpc *h, T *llr, int64_t batch, int n_iters, int spa, ui
             if (bulk_smem > 200 * 1024) {
                 use_bulk = false;
             } else {
-                e = cudaFuncSetAttribute(bulk::cn_bulk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem);
-                if (e != cudaSuccess) { ws.release(); return record_cuda_error(e, "cudaFuncSetAttribute", __FILE__, __LINE__); }
+                { const int rc_ = ensure_dyn_smem(reinterpret_cast<const void *>(bulk::cn_bulk_kernel<T>), bulk_smem); if (rc_) { ws.release(); return rc_; } }
                 const DeviceProps &dp = device_props();
                 const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(220 * 1024) / (bulk_smem + 1024)));
                 int64_t want = (int64_t)(dp.sm_count > 0 ? dp.sm_count : 148) * per_sm;

@@ -782,14 +782,7 @@ static int launch(const Params &p, cudaStream_t st)
     void (*kern)(const Params) = (IOP == 1) ? viterbi_fast_kernel_hard_packed<CODE>
                                : (IOP == 2) ? viterbi_fast_kernel_soft_punct<CODE>
                                : (PACK == 2) ? viterbi_fast_kernel_hard<CODE> : viterbi_fast_kernel_soft<CODE>;
-    static thread_local size_t attr_set[64] = {0};       // per device: largest dynamic smem size already opted in
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) dev = 0;
-    if (attr_set[dev] < smem) {
-        CPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[dev] = smem;
-    }
+    { const int rc_ = ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem); if (rc_) return rc_; }
     const int64_t grid = ceil_div(p.batch, (int64_t)BD * PACK);
     kern<<<(unsigned)grid, BD, smem, st>>>(p);
     CPB_LAUNCH_CHECK();
@@ -1144,8 +1137,8 @@ int cpb_viterbi_decode(const cpbTrellis *t, const void *coded_dev, int in_dtype,
     if (rc) return rc;
     const size_t smem = sizeof(float) * ((size_t)2 * t->S + (1u << t->n)) * gen::BD;
     if (smem > dp.smem_optin) { ws.release(); return CPB_EUNSUPPORTED; }
-    cudaError_t e = cudaFuncSetAttribute(gen::viterbi_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { ws.release(); return record_cuda_error(e, "cudaFuncSetAttribute", __FILE__, __LINE__); }
+    { const int rc_ = ensure_dyn_smem(reinterpret_cast<const void *>(gen::viterbi_generic_kernel), smem); if (rc_) { ws.release(); return rc_; } }
+    cudaError_t e = cudaSuccess;
     for (int64_t f0 = 0; f0 < batch; f0 += stride) {
         gen::Params p{};
         p.coded = coded_dev; p.in_dtype = in_dtype; p.n_in = n_in; p.frame0 = f0;
