@@ -368,6 +368,8 @@ class TurboWorkload(Workload):
     def describe(self):
         return {"workload": self.name, "code": "rate-1/3 turbo, 2 x RSC K=4 (1, 15/13 octal), RandInterlv(6144, seed 1)",
                 "info_bits": self.N, "iterations": self.iters, "codewords_per_step_all_gpus": self.total,
+                "map_window": "commpy_b200.channelcoding.suggest_map_window(codewords per GPU, N): 1024 steps at 8,192 "
+                              "codewords per GPU, 128 at 1,024 (CPB_OPT_BCJR_WINDOW; 96 warm-up steps either side always)",
                 "channel": "BPSK AWGN Eb/N0=1.0 dB, all-zero codewords", "alg_bytes_per_codeword": self.alg_bytes,
                 "l2": "inputs of one step (%.0f MB over all GPUs) exceed the 126 MB L2" % (3 * self.total * self.N * 4 / 1e6)}
 
@@ -382,6 +384,9 @@ class TurboWorkload(Workload):
         self.il = RandInterlv(self.N, 1)
         lo, hi = parallel.shard_range(self.total, rank, world)
         self.batch = hi - lo
+        from commpy_b200.channelcoding import set_map_window, suggest_map_window
+        self.window = suggest_map_window(self.total // world, self.N)        # the same on every rank
+        set_map_window(self.window)
         self.s2 = 1.0 / (2 * (1 / 3) * 10 ** (1.0 / 10))
         g = torch.Generator(device="cuda")
         g.manual_seed(2000 + rank)
@@ -413,7 +418,8 @@ class TurboWorkload(Workload):
                 "api": "commpy_b200.channelcoding.turbo_decode_batch_host(pinned host arrays) -> cpb_turbo_decode_host"}
 
     def e2e_step(self):
-        from commpy_b200.channelcoding import turbo_decode_batch_host
+        from commpy_b200.channelcoding import set_map_window, suggest_map_window, turbo_decode_batch_host
+        set_map_window(suggest_map_window(min(self.batch, 2048), self.N))     # the host pipeline decodes chunks of <= 2,048 codewords
         self.e2e_bits = turbo_decode_batch_host(self.h_np[0], self.h_np[1], self.h_np[2], self.trellis, self.s2, self.iters, self.il)
 
     def e2e_alt(self):

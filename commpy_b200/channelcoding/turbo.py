@@ -17,7 +17,7 @@ from .. import _lib
 from .convcode import _trellis_handle, conv_encode
 
 __all__ = ["turbo_encode", "map_decode", "turbo_decode", "map_decode_batch", "turbo_decode_batch", "map_decode_batch_host",
-           "turbo_decode_batch_host"]
+           "turbo_decode_batch_host", "suggest_map_window", "set_map_window"]
 
 
 def turbo_encode(msg_bits, trellis1, trellis2, interleaver):
@@ -99,6 +99,21 @@ def turbo_decode_batch_host(sys_symbols, non_sys_symbols_1, non_sys_symbols_2, t
                                            _lib.ptr(la), _lib.ptr(bits))
     _lib.check(rc, "turbo_decode")
     return bits
+
+
+def suggest_map_window(batch, N, target_threads=49152):
+    """MAP window length (trellis steps per thread) that fills one B200 for `batch` frames of N steps: the kernels give every
+    (frame, window) its own thread, so a small batch wants shorter windows (each pays 96 warm-up steps either side).
+    Pass the result to `set_map_window`; the library default (1024) does not look at the batch, so that a frame decodes
+    identically whatever it is batched with -- pinning ANY fixed window keeps that property."""
+    nwin = max(1, -(-int(target_threads) // max(1, int(batch))))
+    w = (int(N) // nwin) // 8 * 8
+    return int(min(1024, max(128, w)))
+
+
+def set_map_window(steps):
+    """cpb_set_option(CPB_OPT_BCJR_WINDOW): 0 restores the default (1024-step windows)."""
+    _lib.set_option(_lib.OPT_BCJR_WINDOW, int(steps))
 
 
 def _checked_perm(interleaver, N):

@@ -756,7 +756,17 @@ static bool matches(const int32_t *next, const int32_t *out, int S)
     return true;
 }
 
-static int nwindows(int N) { return (N > WIN + WIN / 2) ? (int)ceil_div(N, WIN) : 1; }
+// steps per window: 1024 unless cpb_set_option(CPB_OPT_BCJR_WINDOW, w) asks for shorter windows (a multiple of 8, >= 128):
+// more threads per frame for small batches at the price of more warm-up steps.  The split depends only on N and this
+// explicit option, never on the batch, so a frame decodes identically whatever it is batched with.
+static int window_len()
+{
+    int w = option(CPB_OPT_BCJR_WINDOW);
+    if (w <= 0) return WIN;
+    w = (w / 8) * 8;
+    return std::min(WIN, std::max(128, w));
+}
+static int nwindows(int N) { const int w = window_len(); return (N > w + w / 2) ? (int)ceil_div(N, w) : 1; }
 
 template <class T>
 static int launch(const Params &p, bool vec, cudaStream_t st)
@@ -897,7 +907,7 @@ __global__ void __launch_bounds__(256) scatter_bits_kernel(const uint8_t *__rest
 static size_t beta_floats(int64_t frames, int N, int S)
 {
     const int nwin = tpf::nwindows(N);
-    const int win = (nwin == 1) ? N : tpf::WIN;
+    const int win = (nwin == 1) ? N : tpf::window_len();
     const int64_t bp = ceil_div(frames, 32) * 32;
     const size_t a = (size_t)frames * (N + 1) * S;
     const size_t b = (size_t)nwin * bp * win * S;
@@ -913,7 +923,7 @@ static int launch_map(const cpbTrellis *t, int S, const float *sys, const float 
     {
         tpf::Params p{};
         p.sys = sys; p.par = par; p.La = La; p.batch = batch; p.bp = ceil_div(batch, 32) * 32;
-        p.N = N; p.nwin = tpf::nwindows(N); p.win = (p.nwin == 1) ? N : tpf::WIN;
+        p.N = N; p.nwin = tpf::nwindows(N); p.win = (p.nwin == 1) ? N : tpf::window_len();
         p.c = tpf::LOG2E / noise_var; p.mode = mode; p.beta = beta; p.NT = (int64_t)p.nwin * p.bp;
         p.L_out = L_out; p.bits_out = bits;
         const bool vec = (N % 4 == 0) && ((((uintptr_t)sys | (uintptr_t)par | (uintptr_t)La | (uintptr_t)L_out) & 15) == 0) &&

@@ -45,6 +45,8 @@ int cpb_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *global_
  * environment.  They select between kernels that implement the SAME reference semantics. */
 #define CPB_OPT_VITERBI_FORCE_GENERIC 0   /* 1: every trellis goes through the table-driven Viterbi kernel */
 #define CPB_OPT_LDPC_NO_BULK 1            /* 1: min-sum check pass without the bulk-copy staged kernel    */
+#define CPB_OPT_BCJR_WINDOW 2             /* w > 0: MAP windows of w trellis steps (multiple of 8, 128..1024; default 1024): more
+                                             parallelism per frame for small batches, 96-step warm-up either side as always */
 #define CPB_OPT_COUNT 8
 int cpb_set_option(int option_id, int value);
 int cpb_get_option(int option_id, int *value);
