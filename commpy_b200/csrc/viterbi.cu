@@ -311,9 +311,18 @@ __device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int t
 #pragma unroll
     for (int fi = 0; fi < PACK; ++fi) hi_sh[fi] = (uint32_t)(te - ts) << 17;
     const int scratch = sm.tasks + (TASK_CAP + lane) * 8;
-    auto check = [&](int tau, int j, uint32_t bw) {
+    // per frame and block of 4 windows: lane | fi << 5 | ring slot of the next jump << 6 | boundary below the block << 22
+    // (hoisted out of the per-window work: it changes only at a jump)
+    uint32_t tcb[PACK];
+    auto block_const = [&](int t0_rel) {
+#pragma unroll
+        for (int fi = 0; fi < PACK; ++fi)
+            tcb[fi] = (uint32_t)lane | ((uint32_t)fi << 5) | (((uint32_t)jw[fi].rowoff / (uint32_t)Jumper<PACK, uint32_t>::ROWB) << 6) |
+                      ((uint32_t)(t0_rel >> 2) << 22);
+    };
+    // tl = tau - ts of the window, as tl12 = tl << 12
+    auto check = [&](uint32_t tl12, int j, uint32_t bw) {
         const uint32_t msk = 63u << (j + 1);
-        const uint32_t twc = (uint32_t)lane | ((uint32_t)(tau - ts) << 12) | ((uint32_t)((tau - 1 - j - ts) >> 2) << 22);
 #pragma unroll
         for (int fi = 0; fi < PACK; ++fi) {
             const uint32_t b = (bw >> (16 * fi)) & 0x3FFu;
@@ -322,10 +331,8 @@ __device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int t
             const int qi = ntask + __popc(vote & lt_mask);
             ntask += __popc(vote);
             // retire the path (it served the windows (tau, hi]) and start the one of best[tau]
-            sm_at<uint2>(miss ? sm.tasks + qi * 8 : scratch) = make_uint2(
-                twc | ((uint32_t)fi << 5) | (((uint32_t)jw[fi].rowoff / (uint32_t)Jumper<PACK, uint32_t>::ROWB) << 6) | hi_sh[fi],
-                jw[fi].reg);
-            hi_sh[fi] = miss ? ((uint32_t)(tau - ts) << 17) : hi_sh[fi];
+            sm_at<uint2>(miss ? sm.tasks + qi * 8 : scratch) = make_uint2(tcb[fi] | tl12 | hi_sh[fi], jw[fi].reg);
+            hi_sh[fi] = miss ? (tl12 << 5) : hi_sh[fi];
             jw[fi].reg = miss ? b : jw[fi].reg;
         }
     };
@@ -338,18 +345,21 @@ __device__ __forceinline__ void tb_block_body(const Smem<PACK> sm, int ts, int t
     };
     // ---- phase A: the rest of the block that holds te, then whole blocks down to ts
     int tau = te - 1;
+    block_const(te - 1 - jte - ts);
     for (int j = jte - 1; j >= 0; --j, --tau)
-        check(tau, j, (j == 0) ? bq.x : (j == 1) ? bq.y : bq.z);
+        check((uint32_t)(tau - ts) << 12, j, (j == 0) ? bq.x : (j == 1) ? bq.y : bq.z);
     while (tau > ts) {
         make_room();
 #pragma unroll
         for (int fi = 0; fi < PACK; ++fi) jw[fi].jump();
         bfo -= BD * 16;
         bq = sm_at<uint4>(bfo);
-        check(tau, 3, bq.w);
-        check(tau - 1, 2, bq.z);
-        check(tau - 2, 1, bq.y);
-        check(tau - 3, 0, bq.x);
+        block_const(tau - 4 - ts);
+        const uint32_t tl12 = (uint32_t)(tau - ts) << 12;
+        check(tl12, 3, bq.w);
+        check(tl12 - (1u << 12), 2, bq.z);
+        check(tl12 - (2u << 12), 1, bq.y);
+        check(tl12 - (3u << 12), 0, bq.x);
         tau -= 4;
     }
     // ---- closing paths of this thread's own frames (interleaved for ILP); the walk above ended at boundary ts
@@ -422,6 +432,12 @@ __device__ __noinline__ void tb_block_call(const Smem<PACK> sm, int ts, int te, 
 }
 #ifndef CPB_QD_HARD
 #define CPB_QD_HARD 4              // input prefetch distance of the hard kernel, in pairs of steps
+#endif
+#ifndef CPB_QD_SOFT
+#define CPB_QD_SOFT 2              // input prefetch distance of the soft kernels, in pairs of steps
+#endif
+#ifndef CPB_SOFT_MIN_CTAS
+#define CPB_SOFT_MIN_CTAS 12       // __launch_bounds__ minimum CTAs per SM of the soft kernels (caps them at 168 registers)
 #endif
 #ifndef CPB_TB_DEPHASE
 #define CPB_TB_DEPHASE 8           // windows in the first traceback block of the second warp of a scheduler (0: off)
@@ -736,10 +752,10 @@ template <class CODE>
 __global__ void __launch_bounds__(BD) viterbi_fast_kernel_hard_packed(const Params p) { viterbi_fast_body<CODE, 2, CPB_QD_HARD, 1>(p); }
 // soft / unquantized: one frame per thread, 32-bit keys
 template <class CODE>
-__global__ void __launch_bounds__(BD, 12) viterbi_fast_kernel_soft(const Params p) { viterbi_fast_body<CODE, 1, 2, 0>(p); }
+__global__ void __launch_bounds__(BD, CPB_SOFT_MIN_CTAS) viterbi_fast_kernel_soft(const Params p) { viterbi_fast_body<CODE, 1, CPB_QD_SOFT, 0>(p); }
 // the same on punctured rows: depuncturing (convcode.py:777-804) happens in the load
 template <class CODE>
-__global__ void __launch_bounds__(BD, 12) viterbi_fast_kernel_soft_punct(const Params p) { viterbi_fast_body<CODE, 1, 2, 2>(p); }
+__global__ void __launch_bounds__(BD, CPB_SOFT_MIN_CTAS) viterbi_fast_kernel_soft_punct(const Params p) { viterbi_fast_body<CODE, 1, CPB_QD_SOFT, 2>(p); }
 
 // Per-frame power-of-two scale for float input: the largest |value| of the frame (after the +-500 clip in 'soft'
 // mode, convcode.py:718-719; including the -1 padding of 'unquantized', :729-732) maps to at most 2^QBITS.
