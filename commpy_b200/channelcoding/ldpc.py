@@ -22,6 +22,10 @@ def build_matrix(ldpc_code_params):
     The generator is valid for triangular systematic codes only, like the reference's."""
     import scipy.sparse.linalg as splg
     n_c = ldpc_code_params["n_cnodes"]
+    if ldpc_code_params.get("parity_check_matrix") is not None and "cnode_adj_list" not in ldpc_code_params:
+        H = sp.csc_matrix(ldpc_code_params["parity_check_matrix"])     # dict built from a matrix: only the generator is missing
+        ldpc_code_params["generator_matrix"] = splg.inv(H[:, -n_c:]).dot(H[:, :-n_c]).tocsr()
+        return
     deg = np.asarray(ldpc_code_params["cnode_deg_list"])
     adj = np.asarray(ldpc_code_params["cnode_adj_list"]).reshape((n_c, ldpc_code_params["max_cnode_deg"]))
     rows = np.repeat(np.arange(n_c), deg)

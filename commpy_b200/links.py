@@ -20,7 +20,7 @@ import numpy as np
 
 from . import _lib, parallel
 
-__all__ = ["link_performance", "LinkModel", "AwgnSisoChannel", "ConvLinkGPU", "conv_link_tx"]
+__all__ = ["link_performance", "LinkModel", "AwgnSisoChannel", "ConvLinkGPU", "conv_link_tx", "idd_decoder"]
 
 
 class AwgnSisoChannel:
@@ -440,3 +440,22 @@ class TurboLinkGPU:
                     break
             BERs[i] = c[0] / c[2]
         return BERs
+
+
+def idd_decoder(detector, decoder, decision, n_it):
+    """Iterative detection and decoding for a coded MIMO link (links.py:345-407): returns the 6-argument decoder LinkModel
+    calls.  Each iteration decodes the current a-priori LLRs, hands the extrinsic part to `detector(y_i, H_i, constellation,
+    noise_var, a_priori_i)` vector by vector, and keeps the detector's extrinsic for the next round; `decision` maps the
+    final LLRs to bits."""
+    def decode(y, h, constellation, noise_var, a_priori, bits_per_send):
+        to_decoder = np.array(a_priori, dtype=float)
+        nb_vect = h.shape[0]
+        to_detector = np.zeros_like(to_decoder)
+        for _ in range(n_it):
+            to_detector = decoder(to_decoder) - to_decoder
+            for i in range(nb_vect):
+                sl = slice(i * bits_per_send, (i + 1) * bits_per_send)
+                to_decoder[sl] = detector(y[i], h[i], constellation, noise_var, to_detector[sl])
+            to_decoder -= to_detector
+        return decision(to_decoder + to_detector)
+    return decode

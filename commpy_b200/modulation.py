@@ -2,7 +2,8 @@
 
 Mirror of commpy/modulation.py:39-262 (Modem, PSKModem, QAMModem).  `demodulate` runs in CUDA
 (commpy_b200/csrc/demap.cu) through `cpb_demod_soft` / `cpb_demod_hard`; there is no CPU demapper.
-OFDM helpers and the MIMO tree-search detectors of the reference are outside the decoding hot path.
+The MIMO tree-search detectors (kbest, best_first_detector, max_log_approx, bit_lvl_repr: :325-646) are host-side mirrors
+(callers of the decoders in coded MIMO links); OFDM helpers are outside the decoding path.
 """
 import ctypes as C
 
@@ -11,7 +12,7 @@ import numpy as np
 from . import _lib
 from .utilities import signal_power
 
-__all__ = ["Modem", "PSKModem", "QAMModem"]
+__all__ = ["Modem", "PSKModem", "QAMModem", "kbest", "best_first_detector", "max_log_approx", "bit_lvl_repr"]
 
 
 class _ModemBox:
@@ -161,3 +162,147 @@ class QAMModem(Modem):
         imag = np.tile(np.hstack((pam, pam[::-1])), side // 2)
         real = pam.repeat(side)
         super().__init__(imag * 1j + real)
+
+
+# ----------------------------------------------------------------------------------------------------
+# MIMO detectors (host side): callers of the decoders in coded MIMO links, SURVEY 8(f) row 4.
+# Tree searches over the QR-decomposed channel; they feed LLRs to the GPU decoders (ldpc_bp_decode, ...).
+# ----------------------------------------------------------------------------------------------------
+def max_log_approx(y, h, noise_var, pts_list, demode):
+    """Max-log LLRs from a list of candidate symbol vectors (modulation.py:599-646): for every bit,
+    -(min_{bit=0} |y - H x|^2 - min_{bit=1} |y - H x|^2) / (2 noise_var); an empty side counts as +inf."""
+    pts_list = np.asarray(pts_list)
+    npts = pts_list.shape[1]
+    words = np.asarray(demode(pts_list.reshape(-1, order="F"))).reshape(npts, -1)
+    dist = np.sum(np.abs(np.asarray(y)[:, None] - np.asarray(h).dot(pts_list)) ** 2, axis=0)
+    llr = np.empty(words.shape[1])
+    for k in range(words.shape[1]):
+        d0 = dist[words[:, k] == 0]
+        d1 = dist[words[:, k] == 1]
+        llr[k] = (d0.min() if d0.size else np.inf) - (d1.min() if d1.size else np.inf)
+    return -llr / (2 * noise_var)
+
+
+def kbest(y, h, constellation, K, noise_var=0, output_type="hard", demode=None):
+    """MIMO K-best (breadth-first) detection on the QR-decomposed channel (modulation.py:325-419): level by level from the
+    last transmit antenna, every surviving candidate is extended by every constellation point and the K smallest partial
+    distances survive.  'hard' returns the best symbol vector, 'soft' the max-log LLRs over the final survivors."""
+    h = np.asarray(h)
+    rows, cols = h.shape
+    if cols > rows:
+        raise ValueError("h has more columns than rows")
+    if output_type not in ("hard", "soft"):
+        raise ValueError('output_type must be "hard" or "soft"')
+    q, r = np.linalg.qr(h)
+    yt = q.conj().T.dot(y)
+    cst = np.asarray(constellation)
+    m = len(cst)
+    cand = np.zeros((cols, 1), dtype=complex if np.iscomplexobj(cst) else float)
+    resid = np.array(yt, dtype=complex)[:, None]
+    dist = np.zeros(1)
+    for level in range(cols - 1, -1, -1):
+        ncand = cand.shape[1]
+        cand = np.tile(cand, (1, m))
+        resid = np.tile(resid, (1, m))
+        hyp = np.repeat(cst, ncand)                          # point i for all candidates, then point i+1, ...
+        cand[level] = hyp
+        resid[level] = resid[level] - r[level, level] * hyp
+        dist = np.tile(dist, m) + np.abs(resid[level]) ** 2
+        keep = np.argsort(dist)[:K]
+        cand, resid, dist = cand[:, keep], resid[:, keep], dist[keep]
+        resid[:level] = resid[:level] - r[:level, level, None] * hyp[keep]
+    if output_type == "hard":
+        return cand[:, 0]
+    return max_log_approx(y, h, noise_var, cand, demode)
+
+
+class _TreeNode:
+    """A node of the detection tree with lazy access to its next-best sibling: `order` indexes the parent's children by
+    increasing partial metric."""
+    __slots__ = ("vec", "metric", "_vecs", "_metrics", "_k")
+
+    def __init__(self, vecs, metrics, k=0):
+        self._vecs, self._metrics, self._k = vecs, metrics, k
+        self.vec = vecs[:, k]
+        self.metric = metrics[k]
+
+    def sibling(self):
+        return _TreeNode(self._vecs, self._metrics, self._k + 1) if self._k + 1 < len(self._metrics) else None
+
+    def best_child(self, yt, r, cst):
+        depth = self.vec.size + 1                              # symbols fixed in a child, counted from the last antenna
+        vecs = np.empty((depth, cst.size), dtype=cst.dtype)
+        vecs[0] = cst
+        vecs[1:] = self.vec[:, None]
+        metrics = np.abs(yt[-depth] - r[-depth, -depth:].dot(vecs)) ** 2 + self.metric
+        order = np.argsort(metrics)
+        return _TreeNode(vecs[:, order], metrics[order])
+
+
+def best_first_detector(y, h, constellation, stack_size, noise_var, demode, llr_max):
+    """MIMO best-first (stack) detection with max-log LLR output (modulation.py:422-565; He, Zhang, Liang, IEEE TVLSI 2019).
+
+    One sorted stack per tree level; every sweep pops the best node of each level, re-inserts its next sibling and pushes its
+    best child one level down when they lie inside the current search radius, then folds a reached leaf into the MAP /
+    counter-hypothesis metrics; the stacks are cut to `stack_size` after every sweep.  Returns
+    (metric_MAP - metric_counter-hypothesis) * (+-1 of the MAP bit) per bit, clipped to +-llr_max."""
+    from bisect import bisect_right
+    h = np.asarray(h)
+    n = h.shape[0]
+    cst = np.array(constellation)
+    nbits = int(np.log2(cst.size))
+    q, r = np.linalg.qr(h)
+    yt = q.conj().T.dot(y)
+    map_metric, map_bits = np.inf, None
+    counter = np.full((n, nbits), np.inf)
+    stacks = [[] for _ in range(n)]                            # stacks[i]: nodes with n - i symbols fixed; stacks[0]: leaves
+
+    def push(stack, node):                                     # sorted by partial metric, after equal ones (bisect.insort)
+        stack.insert(bisect_right([nd.metric for nd in stack], node.metric), node)
+
+    def signed_bits(vec):
+        b = np.asarray(demode(vec)).reshape(-1, nbits).astype(float)
+        b[b == 0] = -1
+        return b
+
+    root = _TreeNode(np.empty((0, 1), dtype=cst.dtype), np.zeros(1))
+    stacks[-1].append(root.best_child(yt, r, cst))
+    while any(stacks[1:]):
+        for lower in range(n - 1):
+            level = lower + 1
+            if not stacks[level]:
+                continue
+            node = stacks[level].pop(0)
+            if map_bits is None:
+                radius = np.inf                                # no leaf yet: keep everything
+            else:
+                differs = map_bits[level:] != signed_bits(node.vec)
+                sel = counter[level:][differs]
+                radius = max(counter[:level].max(), sel.max() if sel.size else np.inf)
+            sib = node.sibling()
+            if sib is not None and sib.metric <= radius:
+                push(stacks[level], sib)
+            child = node.best_child(yt, r, cst)
+            if child.metric <= radius:
+                push(stacks[lower], child)
+        if stacks[0]:
+            leaf = stacks[0][0]
+            if leaf.metric < map_metric:
+                np.minimum(counter, map_metric, out=counter)
+                map_metric = leaf.metric
+                map_bits = signed_bits(leaf.vec)
+            else:
+                np.minimum(counter, leaf.metric, out=counter)
+            np.clip(counter, map_metric - llr_max, map_metric + llr_max, out=counter)
+        stacks[0].clear()
+        for lower in range(n - 1):
+            del stacks[lower + 1][stack_size[lower]:]
+    return ((map_metric - counter) * map_bits).reshape(-1)
+
+
+def bit_lvl_repr(H, w):
+    """Channel matrix of the bit-level representation: H (I_n kron w) for an even number of weights (modulation.py:568-596)."""
+    if len(w) % 2:
+        raise ValueError("Beta (length of w) must be even.")
+    H = np.asarray(H)
+    return H.dot(np.kron(np.eye(H.shape[1]), w))

@@ -78,3 +78,53 @@ def test_ldpc_and_demapper_fresh_cases(ref):
     fin = np.isfinite(want)
     assert np.allclose(want[fin], got[fin], rtol=1e-9, atol=1e-9), seed
     assert np.array_equal(modem.demodulate(y, "hard"), oracle.demodulate(modem, y, "hard")), seed
+
+
+def test_mimo_mirrors_fresh_cases(ref):
+    """host-side MIMO mirrors (kbest, best_first_detector, idd_decoder) against the live reference on fresh draws"""
+    import importlib
+    _, rmod = ref
+    rlinks = importlib.import_module("commpy.links")
+    from commpy_b200 import modulation as mod
+    from commpy_b200.links import idd_decoder
+    seed = _seed()
+    rs = np.random.RandomState(seed)
+    for m, n in ((4, 2), (16, 3), (16, 4)):
+        rq = rmod.QAMModem(m)
+        mq = mod.QAMModem(m)
+        np.testing.assert_array_equal(rq.constellation, mq.constellation)
+
+        def demode(s):
+            return rq.demodulate(s, "hard")
+        for _ in range(10):
+            nb = rq.num_bits_symbol
+            h = (rs.randn(n, n) + 1j * rs.randn(n, n)) * np.sqrt(0.5)
+            nv = n / 10 ** (rs.uniform(5, 25) / 10)
+            y = h.dot(rq.modulate(rs.randint(0, 2, n * nb))) + (rs.randn(n) + 1j * rs.randn(n)) * np.sqrt(nv / 2)
+            msg = "seed %d" % seed
+            np.testing.assert_allclose(mod.kbest(y, h, mq.constellation, 6), rmod.kbest(y, h, rq.constellation, 6), atol=1e-12,
+                                       err_msg=msg)
+            np.testing.assert_allclose(mod.kbest(y, h, mq.constellation, 6, nv, "soft", demode),
+                                       rmod.kbest(y, h, rq.constellation, 6, nv, "soft", demode), rtol=1e-9, atol=1e-9, err_msg=msg)
+            stack = tuple(rs.randint(1, 6, n - 1))
+            np.testing.assert_allclose(mod.best_first_detector(y, h, mq.constellation, stack, nv, demode, 100),
+                                       rmod.best_first_detector(y, h, rq.constellation, stack, nv, demode, 100), rtol=1e-9,
+                                       atol=1e-9, err_msg=msg)
+    # idd_decoder: same closures through both, 3 iterations
+    rq = rmod.QAMModem(16)
+
+    def detector(y, h, constellation, noise_var, a_priori):
+        return rmod.kbest(y, h, constellation, 8, noise_var, "soft", lambda s: rq.demodulate(s, "hard")) + 0.25 * a_priori
+
+    def decoder(llr):
+        return np.tanh(llr) * 3 + np.roll(llr, 1)
+
+    def decision(llr):
+        return (llr > 0).astype(int)
+    nvec, n = 5, 2
+    h = (rs.randn(nvec, n, n) + 1j * rs.randn(nvec, n, n)) * np.sqrt(0.5)
+    y = np.einsum("ijk,ik->ij", h, rq.modulate(rs.randint(0, 2, nvec * n * 4)).reshape(nvec, n)) + 0.1 * rs.randn(nvec, n)
+    ap = rs.randn(nvec * n * 4)
+    got = idd_decoder(detector, decoder, decision, 3)(y, h, rq.constellation, 0.02, ap.copy(), n * 4)
+    want = rlinks.idd_decoder(detector, decoder, decision, 3)(y, h, rq.constellation, 0.02, ap.copy(), n * 4)
+    np.testing.assert_array_equal(got, want)
