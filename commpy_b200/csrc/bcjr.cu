@@ -206,6 +206,10 @@ struct Params {
     float *L_out;
     uint8_t *bits_out;
     int ext;                     // map_lin_kernel only: L_out receives L - La (the extrinsic turbo_decode forms, turbo.py:318,328)
+    // step-major arrays (map_lin2_kernel<T, true>, the turbo loop): element (step t, frame f) at [row(t) * pitch + f];
+    // sys, La, L_out and bits_out use row(t) = rmap ? rmap[t] : t (the interleaver, interleavers.py:13-47), par uses row t
+    int64_t pitch;
+    const int32_t *rmap;
 };
 
 template <class T, int G>     // G = steps per vector access (4: float4 / uchar4, 1: scalar)
@@ -739,6 +743,450 @@ __global__ void __launch_bounds__(128) map_lin_kernel(const Params p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Block-normalised form of map_lin_kernel for SYSTEMATIC trellises (output MSB = input bit: every 'rsc' Trellis and the
+// config-3 code) -- the same thread mapping, windows, checkpoints and prefetching, ~40 % fewer instructions per step:
+//   * prior, systematic and parity observation are folded into FOUR weights per step, g[u][cp] = 2^-(what opposes the best
+//     (u, cp)), computed once per sweep (2 ex2); the forward sweep keeps them in shared memory for the beta
+//     recomputation AND the alpha / a-posteriori step (map_lin_kernel evaluated its 3 ex2 three times per step);
+//   * the metrics are rescaled every FOURTH step instead of every step.  Scaling is arbitrary in exact arithmetic
+//     (turbo.py:110-111,155 divide by the sum only to stay in range), and fp32 has the range for 4 steps of typical decay;
+//     a block whose metric sum falls below 2^-20 is redone with per-step scaling from the saved metrics, so a run of
+//     strongly contradicted observations (weights down to 2^-300 per step) cannot underflow;
+//   * the a-posteriori sums include the prior (one multiply per edge less); L = La + ln2 (lg2 a1 - lg2 a0 - l), with l the
+//     clamped log2 prior odds that went into the weights.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__host__ __device__ constexpr bool systematic()
+{
+    for (int s = 0; s < T::S; ++s)
+        for (int u = 0; u < 2; ++u)
+            if ((T::out(s, u) >> 1) != u) return false;
+    return true;
+}
+
+constexpr float RESCALE_FLOOR = 9.5367431640625e-07f;      // 2^-20
+#ifndef CPB_MAP_PFF
+#define CPB_MAP_PFF 1              // forward sweep: segments (of 8 steps, with their beta checkpoint) in flight per thread
+#endif
+constexpr int PFF = CPB_MAP_PFF;
+
+#ifndef CPB_MAP_MINB
+#define CPB_MAP_MINB 12            // __launch_bounds__ minimum CTAs (= warps) per SM of map_lin2_kernel: <= 168 registers, three
+                                   // warps per scheduler; the 1,536 warps of a config-3 pass (8,192 x 6 windows) are one wave
+#endif
+template <class T, bool SM>      // SM: step-major arrays (Params::pitch / rmap)
+__global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params p)
+{
+    constexpr int S = T::S;
+    constexpr int G = 4;
+    constexpr int SV = S / 4;                   // float4 words per metric vector
+    static_assert(S % 4 == 0 && systematic<T>(), "systematic trellis with 4 or 8 states");
+    extern __shared__ float4 smem_v[];
+    const int tid = threadIdx.x, bd = blockDim.x;
+    float4 *sb = smem_v;                        // [CK][SV][bd]  beta of the current segment
+    float4 *sg = smem_v + CK * SV * bd;         // [CK][bd]      the four branch weights of a step
+    float *sl = reinterpret_cast<float *>(sg + CK * bd);   // [CK][bd]  L_int of a step
+    const int64_t g = (int64_t)blockIdx.x * bd + tid;
+    if (g >= p.NT) return;
+    const int w = (int)(g / p.bp);
+    const int64_t f = g - (int64_t)w * p.bp;
+    if (f >= p.batch) return;
+    const int N = p.N;
+    const int lo = w * p.win, hi = min(N, lo + p.win);
+    const float *fs = p.sys + f * N, *fp = p.par + f * N, *fl = p.La + f * N;
+    float *ck = p.beta + g;
+    const float c2 = 2.0f * p.c;
+
+    // weights of the four (u, cp) pairs relative to the most likely pair: index o = u << 1 | cp
+    auto weights = [&](float ys, float yp, float la_raw) -> float4 {
+        const float l = fminf(fmaxf(la_raw * LOG2E, -60.0f), 60.0f);
+        const float lu = fminf(fmaxf(ys * c2, -120.0f), 120.0f) + l;       // log2 odds of u = 1: channel + prior
+        const float lb = fminf(fmaxf(yp * c2, -120.0f), 120.0f);           // log2 odds of cp = 1
+        const float eu = ex2(-fabsf(lu)), eb = ex2(-fabsf(lb));
+        const float u1 = (lu >= 0.0f) ? 1.0f : eu, u0 = (lu >= 0.0f) ? eu : 1.0f;
+        const float q1 = (lb >= 0.0f) ? 1.0f : eb, q0 = (lb >= 0.0f) ? eb : 1.0f;
+        return make_float4(u0 * q0, u0 * q1, u1 * q0, u1 * q1);
+    };
+    auto pick = [](const float4 &v, int o) -> float { return o == 0 ? v.x : (o == 1 ? v.y : (o == 2 ? v.z : v.w)); };
+    auto total = [](const float (&v)[S]) {
+        float sum = v[0];
+#pragma unroll
+        for (int s = 1; s < S; ++s) sum += v[s];
+        return sum;
+    };
+    auto scale = [](float (&v)[S], float sum) {
+        const float r = rcp(fmaxf(sum, 1.0e-37f));
+#pragma unroll
+        for (int s = 0; s < S; ++s) v[s] *= r;
+    };
+    auto beta_raw = [&](float (&B)[S], const float4 &gw) {                  // beta_t -> beta_{t-1}, turbo.py:106-108
+        float Bn[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            Bn[s] = pick(gw, T::out(s, 0)) * B[T::ns(s, 0)] + pick(gw, T::out(s, 1)) * B[T::ns(s, 1)];
+#pragma unroll
+        for (int s = 0; s < S; ++s) B[s] = Bn[s];
+    };
+    // the rows of steps e0+1 .. e0+4 in the step-major arrays
+    auto rows4 = [&](int e0, int (&r)[G]) {
+        if (p.rmap) {
+            const int4 q = __ldg(reinterpret_cast<const int4 *>(p.rmap + e0));
+            r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < G; ++i) r[i] = e0 + i;
+        }
+    };
+    // inputs of steps e0+1 .. e0+4 (0-based elements e0 .. e0+3)
+    auto ld3 = [&](int e0, float (&vs)[G], float (&vp)[G], float (&vl)[G]) {
+        if (SM) {
+            int r[G];
+            rows4(e0, r);
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                vs[i] = __ldg(p.sys + (int64_t)r[i] * p.pitch + f);
+                vp[i] = __ldg(p.par + (int64_t)(e0 + i) * p.pitch + f);
+                vl[i] = __ldg(p.La + (int64_t)r[i] * p.pitch + f);
+            }
+        } else {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(fs + e0));
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(fp + e0));
+            const float4 c = __ldg(reinterpret_cast<const float4 *>(fl + e0));
+            vs[0] = a.x; vs[1] = a.y; vs[2] = a.z; vs[3] = a.w;
+            vp[0] = b.x; vp[1] = b.y; vp[2] = b.z; vp[3] = b.w;
+            vl[0] = c.x; vl[1] = c.y; vl[2] = c.z; vl[3] = c.w;
+        }
+    };
+    // ---- step-major input staging: cp.async straight into shared memory, completion by cp.async groups.  (Register
+    // prefetching does not survive ptxas here: the 12 scalar loads of a group all land on one scoreboard, so the first use
+    // of group n also waited for the loads of group n+1 issued a moment before -- a quarter of all warp samples.)
+    // Ring of RB groups in the beta / weight area (idle during the backward sweep and the alpha warm-up); a slot holds the
+    // 12 floats of a group (sys, par, L_int of 4 steps), float k of slot q at ring[(q * 12 + k) * bd + tid].
+    constexpr int RB = (CK * (S + 5) / 12 >= 8) ? 8 : CK * (S + 5) / 12;          // 8 groups (6 for 4 states)
+    float *ring = reinterpret_cast<float *>(smem_v);
+    float *segbuf = ring + (CK * SV * 4 + CK * 4 + CK) * bd;          // forward sweep: inputs + checkpoint of the NEXT segment
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring) + 4u * tid;
+    const uint32_t seg_s = (uint32_t)__cvta_generic_to_shared(segbuf) + 4u * tid;
+    auto cp4 = [](uint32_t dst, const float *src) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+    };
+    auto commit = []() { asm volatile("cp.async.commit_group;" ::: "memory"); };
+    auto rows_of = [&](int e0) -> int4 {                               // rows of elements e0 .. e0+3
+        return p.rmap ? __ldg(reinterpret_cast<const int4 *>(p.rmap + e0)) : make_int4(e0, e0 + 1, e0 + 2, e0 + 3);
+    };
+    auto issue_group = [&](uint32_t dst, int e0, const int4 &r) {      // 12 floats -> dst + 4 bd k
+        const int rr[G] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            cp4(dst + 4u * bd * i, p.sys + (int64_t)rr[i] * p.pitch + f);
+            cp4(dst + 4u * bd * (4 + i), p.par + (int64_t)(e0 + i) * p.pitch + f);
+            cp4(dst + 4u * bd * (8 + i), p.La + (int64_t)rr[i] * p.pitch + f);
+        }
+    };
+    // a stream of `ng` groups, group n = elements first + n * stride .. +3, through the ring: start() fills the ring,
+    // take(n) waits for group n, hands out its values and refills its slot with group n + RB
+    int4 rnext = make_int4(0, 0, 0, 0);
+    auto stream_start = [&](int first, int stride, int ng) {
+#pragma unroll
+        for (int k = 0; k < RB; ++k) {
+            if (k < ng) issue_group(ring_s + 4u * bd * 12 * k, first + k * stride, rows_of(first + k * stride));
+            commit();
+        }
+        if (RB < ng) rnext = rows_of(first + RB * stride);
+    };
+    auto stream_take = [&](int n, int slot, int first, int stride, int ng, float (&vs)[G], float (&vp)[G], float (&vl)[G]) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(RB - 1) : "memory");
+        const float *q = ring + slot * 12 * bd + tid;
+#pragma unroll
+        for (int i = 0; i < G; ++i) { vs[i] = q[i * bd]; vp[i] = q[(4 + i) * bd]; vl[i] = q[(8 + i) * bd]; }
+        if (n + RB < ng) {
+            issue_group(ring_s + 4u * bd * 12 * slot, first + (n + RB) * stride, rnext);
+            if (n + RB + 1 < ng) rnext = rows_of(first + (n + RB + 1) * stride);
+        }
+        commit();
+    };
+    // four beta steps (newest first: gw[3] is the latest step), rescaled at the end; the per-step form if they decayed
+    auto beta_block = [&](float (&B)[S], const float4 (&gw)[G]) {
+        float B0[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) B0[s] = B[s];
+#pragma unroll
+        for (int i = G - 1; i >= 0; --i) beta_raw(B, gw[i]);
+        float sum = total(B);
+        if (!(sum >= RESCALE_FLOOR)) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) B[s] = B0[s];
+#pragma unroll
+            for (int i = G - 1; i >= 0; --i) { beta_raw(B, gw[i]); scale(B, total(B)); }
+            sum = total(B);
+        }
+        scale(B, sum);
+    };
+
+    // ---- backward sweep with checkpoints (the metrics are scaled to sum 1 at every multiple of 4 steps)
+    {
+        float B[S];
+        const int tb = min(N, hi + WARM);
+#pragma unroll
+        for (int s = 0; s < S; ++s) B[s] = 1.0f / S;                      // beta_N = 1 for all states (:225-226), scale free
+        // The inputs of a group (4 steps) are fetched two groups ahead of their use into one of TWO statically named
+        // register sets, the loop handles both per iteration.  (A rolled loop that rotates the sets by register moves makes
+        // ptxas guard all of them with one scoreboard: the first use then waits for the loads issued half an iteration ago
+        // -- 26 % of all warp samples sat on that instruction.)
+        if constexpr (SM) {
+            const int ng = (tb - lo) / G;
+            stream_start(tb - G, -G, ng);
+            int slot = 0;
+#pragma unroll 1
+            for (int n = 0; n < ng; ++n) {
+                float vs[G], vp[G], vl[G];
+                stream_take(n, slot, tb - G, -G, ng, vs, vp, vl);
+                slot = (slot + 1 == RB) ? 0 : slot + 1;
+                float4 gw[G];
+#pragma unroll
+                for (int i = 0; i < G; ++i) gw[i] = weights(vs[i], vp[i], vl[i]);
+                const int e1 = tb - n * G;
+                if (e1 <= hi && (((e1 - lo) % CK) == 0 || e1 == hi)) {        // beta_{e1}: the checkpoint of segment j
+                    const int j = (e1 - lo + CK - 1) / CK - 1;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) ck[((int64_t)j * S + s) * p.NT] = B[s];
+                }
+                beta_block(B, gw);
+            }
+        } else {
+        float qs[2][G], qp[2][G], ql[2][G];
+        ld3(tb - G, qs[0], qp[0], ql[0]);
+        if (tb - G > lo) ld3(tb - 2 * G, qs[1], qp[1], ql[1]);
+        auto group = [&](int e1, float (&vs)[G], float (&vp)[G], float (&vl)[G]) {
+            float4 gw[G];
+#pragma unroll
+            for (int i = 0; i < G; ++i) gw[i] = weights(vs[i], vp[i], vl[i]);
+            if (e1 - 2 * G > lo) ld3(e1 - 3 * G, vs, vp, vl);
+            if (e1 <= hi && (((e1 - lo) % CK) == 0 || e1 == hi)) {        // beta_{e1}: the checkpoint of segment j
+                const int j = (e1 - lo + CK - 1) / CK - 1;
+#pragma unroll
+                for (int s = 0; s < S; ++s) ck[((int64_t)j * S + s) * p.NT] = B[s];
+            }
+            beta_block(B, gw);
+        };
+#pragma unroll 1
+        for (int e1 = tb; e1 > lo; e1 -= 2 * G) {
+            group(e1, qs[0], qp[0], ql[0]);
+            if (e1 - G > lo) group(e1 - G, qs[1], qp[1], ql[1]);
+        }
+        }
+    }
+    // ---- forward sweep
+    float A[S];
+    const int ta = max(0, lo - WARM);
+#pragma unroll
+    for (int s = 0; s < S; ++s) A[s] = (ta == 0) ? ((s == 0) ? 1.0f : 0.0f) : (1.0f / S);    // alpha_0 = delta(s,0), :220-221
+    // one alpha step; with EMIT the a-posteriori log2 ratio of the step (prior included) from the beta words bt[0..SV)
+    auto alpha_raw = [&](float (&A_)[S], const float4 &gw, const float4 *bt, bool emit, float &D) {
+        float tx[2 * S];
+#pragma unroll
+        for (int e = 0; e < 2 * S; ++e) tx[e] = A_[e >> 1] * pick(gw, T::out(e >> 1, e & 1));
+        if (emit) {
+            float bv[S];
+#pragma unroll
+            for (int v = 0; v < SV; ++v) {
+                const float4 q = bt[v * bd];
+                bv[4 * v] = q.x; bv[4 * v + 1] = q.y; bv[4 * v + 2] = q.z; bv[4 * v + 3] = q.w;
+            }
+            float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                a0 += tx[2 * s] * bv[T::ns(s, 0)];
+                a1 += tx[2 * s + 1] * bv[T::ns(s, 1)];
+            }
+            if (fmaxf(a0, a1) < 9.094947017729282e-13f) {     // both below 2^-40 (contradicted observations): redo the sums 2^80 up
+                a0 = a1 = 0.0f;
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    a0 += (tx[2 * s] * 1.099511627776e12f) * (bv[T::ns(s, 0)] * 1.099511627776e12f);
+                    a1 += (tx[2 * s + 1] * 1.099511627776e12f) * (bv[T::ns(s, 1)] * 1.099511627776e12f);
+                }
+            }
+            D = lg2(fmaxf(a1, 1.0e-37f)) - lg2(fmaxf(a0, 1.0e-37f));
+        }
+#pragma unroll
+        for (int n = 0; n < S; ++n) A_[n] = tx[T::pred(n, 0)] + tx[T::pred(n, 1)];             // :136-138
+    };
+    // step-major: the first segment's inputs and checkpoint are requested before the warm-up, segment j+1's when segment j
+    // has been read out of `segbuf` (32 floats: 2 x 12 inputs, 8 checkpoint values)
+    auto issue_segment = [&](int s0, int j) {
+        const int ns = min(CK, hi - s0);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (h * G < ns) issue_group(seg_s + 4u * bd * 12 * h, s0 + h * G, rows_of(s0 + h * G));
+#pragma unroll
+        for (int s = 0; s < S; ++s) cp4(seg_s + 4u * bd * (24 + s), ck + ((int64_t)j * S + s) * p.NT);
+        commit();
+    };
+    if constexpr (SM) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");   // (only empty groups are pending: the ring's slots are free)
+        if (lo < hi) issue_segment(lo, 0);
+        stream_start(ta, G, (lo - ta) / G);
+    }
+    int wslot = 0;
+    for (int e0 = ta; e0 < lo; e0 += G) {                       // warm-up (no LLRs, no beta)
+        float vs[G], vp[G], vl[G];
+        if constexpr (SM) {
+            stream_take((e0 - ta) / G, wslot, ta, G, (lo - ta) / G, vs, vp, vl);
+            wslot = (wslot + 1 == RB) ? 0 : wslot + 1;
+        } else {
+            ld3(e0, vs, vp, vl);
+        }
+        float4 gw[G];
+#pragma unroll
+        for (int i = 0; i < G; ++i) gw[i] = weights(vs[i], vp[i], vl[i]);
+        float A0[S], dummy;
+#pragma unroll
+        for (int s = 0; s < S; ++s) A0[s] = A[s];
+#pragma unroll
+        for (int i = 0; i < G; ++i) alpha_raw(A, gw[i], nullptr, false, dummy);
+        float sum = total(A);
+        if (!(sum >= RESCALE_FLOOR)) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) A[s] = A0[s];
+#pragma unroll
+            for (int i = 0; i < G; ++i) { alpha_raw(A, gw[i], nullptr, false, dummy); scale(A, total(A)); }
+            sum = total(A);
+        }
+        scale(A, sum);
+    }
+    // the inputs and the beta checkpoint of a segment are fetched while the previous segment is being processed
+    static_assert(CK == 2 * G, "segment = two vector groups");
+    float xin[SM ? 1 : PFF][2][3][G], xck[SM ? 1 : PFF][S];
+    auto fetch_segment = [&](int s0, int j, float (&xi)[2][3][G], float (&xc)[S]) {
+        const int ns = min(CK, hi - s0);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (h * G < ns) ld3(s0 + h * G, xi[h][0], xi[h][1], xi[h][2]);
+#pragma unroll
+        for (int s = 0; s < S; ++s) xc[s] = ck[((int64_t)j * S + s) * p.NT];
+    };
+    if constexpr (!SM) {
+#pragma unroll
+        for (int k = 0; k < PFF; ++k)
+            if (lo + k * CK < hi) fetch_segment(lo + k * CK, k, xin[k], xck[k]);
+    }
+    for (int s0 = lo, j = 0; s0 < hi; s0 += CK, ++j) {
+        const int ns = min(CK, hi - s0);                        // 4 or 8
+        if constexpr (SM) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const float *q = segbuf + tid;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int i = 0; i < G; ++i) xin[0][h][a][i] = q[(h * 12 + a * 4 + i) * bd];
+#pragma unroll
+            for (int s = 0; s < S; ++s) xck[0][s] = q[(24 + s) * bd];
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (h * G < ns) {
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    sg[(h * G + i) * bd + tid] = weights(xin[0][h][0][i], xin[0][h][1][i], xin[0][h][2][i]);
+                    sl[(h * G + i) * bd + tid] = xin[0][h][2][i];
+                }
+            }
+        }
+        float B[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) B[s] = xck[0][s];
+        if constexpr (SM) {
+            if (s0 + CK < hi) issue_segment(s0 + CK, j + 1);
+        } else {
+#pragma unroll
+            for (int k = 0; k + 1 < PFF; ++k) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int i = 0; i < G; ++i) xin[k][h][a][i] = xin[k + 1][h][a][i];
+#pragma unroll
+                for (int s = 0; s < S; ++s) xck[k][s] = xck[k + 1][s];
+            }
+            if (s0 + PFF * CK < hi) fetch_segment(s0 + PFF * CK, j + PFF, xin[PFF - 1], xck[PFF - 1]);
+        }
+        // beta of the segment, backwards from its checkpoint, block by block (beta_{s0+1+k} -> sb[k])
+        auto store_beta = [&](int k, const float (&Bv)[S]) {
+#pragma unroll
+            for (int v = 0; v < SV; ++v) sb[(k * SV + v) * bd + tid] = make_float4(Bv[4 * v], Bv[4 * v + 1], Bv[4 * v + 2], Bv[4 * v + 3]);
+        };
+        for (int h = ns / G - 1; h >= 0; --h) {
+            float B0[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) B0[s] = B[s];
+#pragma unroll
+            for (int i = G - 1; i >= 0; --i) { store_beta(h * G + i, B); beta_raw(B, sg[(h * G + i) * bd + tid]); }
+            float sum = total(B);
+            if (!(sum >= RESCALE_FLOOR)) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) B[s] = B0[s];
+#pragma unroll
+                for (int i = G - 1; i >= 0; --i) {
+                    store_beta(h * G + i, B); beta_raw(B, sg[(h * G + i) * bd + tid]); scale(B, total(B));
+                }
+                sum = total(B);
+            }
+            scale(B, sum);
+        }
+        // alpha / a-posteriori LLRs forwards, block by block
+        for (int h = 0; h < ns / G; ++h) {
+            float A0[S], Dv[G];
+#pragma unroll
+            for (int s = 0; s < S; ++s) A0[s] = A[s];
+#pragma unroll
+            for (int i = 0; i < G; ++i) alpha_raw(A, sg[(h * G + i) * bd + tid], sb + (h * G + i) * SV * bd + tid, true, Dv[i]);
+            float sum = total(A);
+            if (!(sum >= RESCALE_FLOOR)) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) A[s] = A0[s];
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    alpha_raw(A, sg[(h * G + i) * bd + tid], sb + (h * G + i) * SV * bd + tid, true, Dv[i]);
+                    scale(A, total(A));
+                }
+                sum = total(A);
+            }
+            scale(A, sum);
+            float Le[G], Lv[G];                                  // extrinsic L - L_int and the full LLR (:145)
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const float la = sl[(h * G + i) * bd + tid];
+                Le[i] = LN2 * (Dv[i] - fminf(fmaxf(la * LOG2E, -60.0f), 60.0f));
+                Lv[i] = la + Le[i];
+            }
+            const int e0 = s0 + h * G;
+            if (SM) {
+                int r[G];
+                rows4(e0, r);
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    p.L_out[(int64_t)r[i] * p.pitch + f] = p.ext ? Le[i] : Lv[i];
+                    if (p.bits_out) p.bits_out[(int64_t)r[i] * p.pitch + f] = (uint8_t)(p.mode == 1 && Lv[i] > 0.0f);
+                }
+            } else {
+                if (p.ext) *reinterpret_cast<float4 *>(p.L_out + f * N + e0) = make_float4(Le[0], Le[1], Le[2], Le[3]);
+                else *reinterpret_cast<float4 *>(p.L_out + f * N + e0) = make_float4(Lv[0], Lv[1], Lv[2], Lv[3]);
+                if (p.bits_out) {
+                    uchar4 b;
+                    b.x = (p.mode == 1 && Lv[0] > 0.0f); b.y = (p.mode == 1 && Lv[1] > 0.0f);
+                    b.z = (p.mode == 1 && Lv[2] > 0.0f); b.w = (p.mode == 1 && Lv[3] > 0.0f);
+                    *reinterpret_cast<uchar4 *>(p.bits_out + f * N + e0) = b;
+                }
+            }
+        }
+    }
+}
+
 // compile-time trellises this kernel is instantiated for (packed from commpy_b200's Trellis tables)
 using RscK4 = CT<8, 0xedfc96369120ull, 0xc99cc99cu>;         // Trellis([3], [[1, 0o15]], [[0o13]], 'rsc')  (config C3)
 using RscK4Legacy = CT<8, 0xedf5b2a4d120ull, 0xcc9999ccu>;   // Trellis([3], [[1, 0o15]], 0o13, 'rsc')
@@ -764,7 +1212,7 @@ static int window_len()
     int w = option(CPB_OPT_BCJR_WINDOW);
     if (w <= 0) return WIN;
     w = (w / 8) * 8;
-    return std::min(WIN, std::max(128, w));
+    return std::min(4096, std::max(128, w));
 }
 static int nwindows(int N) { const int w = window_len(); return (N > w + w / 2) ? (int)ceil_div(N, w) : 1; }
 
@@ -782,10 +1230,25 @@ static int launch(const Params &p, bool vec, cudaStream_t st)
         { const int rc_ = ensure_dyn_smem(reinterpret_cast<const void *>(map_ckpt_kernel<T>), smem); if (rc_) return rc_; }
         map_ckpt_kernel<T><<<grid, bd, smem, st>>>(p);
 #else
+        if constexpr (systematic<T>() && T::S % 4 == 0) {
+            if (!option(CPB_OPT_BCJR_PER_STEP_SCALING)) {
+                // beta, weights and L_int of a segment; step-major: + the 32 staged floats of the next segment (the beta /
+                // weight area doubles as the input ring of the backward sweep)
+                const size_t smem2 = (size_t)bd * (CK * (T::S / 4 * sizeof(float4) + sizeof(float4) + sizeof(float)) +
+                                                   (p.pitch ? 32 * sizeof(float) : 0));
+                void (*kern)(const Params) = p.pitch ? map_lin2_kernel<T, true> : map_lin2_kernel<T, false>;
+                { const int rc_ = ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem2, p.pitch != 0); if (rc_) return rc_; }
+                kern<<<grid, bd, smem2, st>>>(p);
+                CPB_LAUNCH_CHECK();
+                return CPB_OK;
+            }
+        }
+        if (p.pitch) return CPB_EINVAL;
         { const int rc_ = ensure_dyn_smem(reinterpret_cast<const void *>(map_lin_kernel<T>), smem); if (rc_) return rc_; }
         map_lin_kernel<T><<<grid, bd, smem, st>>>(p);
 #endif
-    } else if (vec) map_tpf_kernel<T, 4><<<grid, 128, 0, st>>>(p);
+    } else if (p.pitch) return CPB_EINVAL;
+    else if (vec) map_tpf_kernel<T, 4><<<grid, 128, 0, st>>>(p);
     else map_tpf_kernel<T, 1><<<grid, 128, 0, st>>>(p);
     CPB_LAUNCH_CHECK();
     return CPB_OK;
@@ -903,6 +1366,53 @@ __global__ void __launch_bounds__(256) scatter_bits_kernel(const uint8_t *__rest
     }
 }
 
+// (batch, N) frame-major floats -> (N, pitch) step-major: the layout the turbo loop works in (every access of the MAP
+// kernel is then a full 128-byte line per warp and the interleaver is a row index, not a data movement)
+__global__ void __launch_bounds__(256) to_step_major_kernel(const float *__restrict__ in, int64_t batch, int N, int64_t pitch,
+                                                            float *__restrict__ out)
+{
+    __shared__ float tile[32][33];
+    const int64_t f0 = (int64_t)blockIdx.y * 32;
+    const int t0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t f = f0 + r;
+        const int t = t0 + tx;
+        tile[r][tx] = (f < batch && t < N) ? in[f * N + t] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int t = t0 + r;
+        const int64_t f = f0 + tx;
+        if (t < N && f < pitch) out[(int64_t)t * pitch + f] = tile[tx][r];
+    }
+}
+
+// (N, pitch) step-major bytes -> (batch, N) frame-major (the decisions of the last MAP pass)
+__global__ void __launch_bounds__(256) bits_to_frame_major_kernel(const uint8_t *__restrict__ in, int64_t batch, int N,
+                                                                  int64_t pitch, uint8_t *__restrict__ out)
+{
+    __shared__ uint8_t tile[128][36];
+    const int64_t f0 = (int64_t)blockIdx.y * 32;
+    const int t0 = blockIdx.x * 128;
+    for (int r = threadIdx.x >> 3; r < 128; r += 32) {           // 8 threads read the 32 bytes of a row
+        const int q = threadIdx.x & 7;
+        const int t = t0 + r;
+        uint32_t w = 0u;
+        if (t < N) w = *reinterpret_cast<const uint32_t *>(in + (int64_t)t * pitch + f0 + 4 * q);
+        *reinterpret_cast<uint32_t *>(&tile[r][4 * q]) = w;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 128; i += 256) {
+        const int fl = i >> 7, tl = i & 127;
+        const int64_t f = f0 + fl;
+        const int t = t0 + tl;
+        if (f < batch && t < N) out[f * N + t] = tile[tl][fl];
+    }
+}
+
 // floats of beta scratch one chunk of `frames` frames needs (whichever kernel runs)
 static size_t beta_floats(int64_t frames, int N, int S)
 {
@@ -916,7 +1426,7 @@ static size_t beta_floats(int64_t frames, int N, int S)
 
 static int launch_map(const cpbTrellis *t, int S, const float *sys, const float *par, const float *La, int64_t batch,
                       int N, float noise_var, int mode, float *beta, float *L_out, uint8_t *bits, cudaStream_t st,
-                      int want_ext = 0, int *did_ext = nullptr)
+                      int want_ext = 0, int *did_ext = nullptr, int64_t pitch = 0, const int32_t *rmap = nullptr)
 {
     const int32_t *hn = nullptr, *ho = nullptr;
     cpb_trellis_host_tables(t, &hn, &ho);
@@ -929,9 +1439,11 @@ static int launch_map(const cpbTrellis *t, int S, const float *sys, const float 
         const bool vec = (N % 4 == 0) && ((((uintptr_t)sys | (uintptr_t)par | (uintptr_t)La | (uintptr_t)L_out) & 15) == 0) &&
                          (bits == nullptr || (((uintptr_t)bits) & 3) == 0);
         p.ext = 0;
+        p.pitch = pitch; p.rmap = rmap;
 #ifndef CPB_BCJR_LOGDOMAIN
         if (want_ext && vec && (p.win % tpf::CK) == 0) p.ext = 1;
 #endif
+        if (pitch && !(vec && (p.win % tpf::CK) == 0 && p.ext)) return CPB_EINVAL;      // step_major_ok() said otherwise
         if (did_ext) *did_ext = p.ext;
         if (tpf::matches<tpf::RscK4>(hn, ho, S)) return tpf::launch<tpf::RscK4>(p, vec, st);
         if (tpf::matches<tpf::RscK4Legacy>(hn, ho, S)) return tpf::launch<tpf::RscK4Legacy>(p, vec, st);
@@ -966,6 +1478,26 @@ static int check_trellis(const cpbTrellis *t, int *S)
     return CPB_OK;
 }
 
+// the turbo loop runs on step-major arrays when the block-rescaled kernel takes the trellis and the frame length
+static bool step_major_ok(const cpbTrellis *t, int S, int N, const int32_t *perm_dev)
+{
+#ifdef CPB_BCJR_LOGDOMAIN
+    return false;
+#else
+    if (option(CPB_OPT_BCJR_PER_STEP_SCALING) || option(CPB_OPT_TURBO_FRAME_MAJOR)) return false;
+    if (N % 4 != 0 || (reinterpret_cast<uintptr_t>(perm_dev) & 15) != 0) return false;
+    const int nwin = tpf::nwindows(N);
+    const int win = (nwin == 1) ? N : tpf::window_len();
+    if (win % tpf::CK != 0) return false;
+    const int32_t *hn = nullptr, *ho = nullptr;
+    cpb_trellis_host_tables(t, &hn, &ho);
+    return (tpf::matches<tpf::RscK4>(hn, ho, S) && tpf::systematic<tpf::RscK4>()) ||
+           (tpf::matches<tpf::RscK4Legacy>(hn, ho, S) && tpf::systematic<tpf::RscK4Legacy>()) ||
+           (tpf::matches<tpf::RscK3Legacy>(hn, ho, S) && tpf::systematic<tpf::RscK3Legacy>()) ||
+           (tpf::matches<tpf::RscK3>(hn, ho, S) && tpf::systematic<tpf::RscK3>());
+#endif
+}
+
 static int64_t chunk_frames(int64_t batch, int N, int S)
 {
     const double per = (double)(N + tpf::WIN + 1) * S * 4.0 + 5.0 * N * 4.0 + N;
@@ -995,7 +1527,8 @@ int cpb_turbo_workspace_bytes(const cpbTrellis *t, int64_t batch, int64_t N, siz
     if (rc) return rc;
     if (!bytes || batch < 0 || N < 1 || N > (1 << 24)) return CPB_EINVAL;
     const int64_t Fc = batch ? bcjr::chunk_frames(batch, (int)N, S) : 0;
-    *bytes = batch ? (bcjr::beta_floats(Fc, (int)N, S) + 5 * (size_t)Fc * N) * sizeof(float) + (size_t)Fc * N + 256 : 0;
+    const size_t nvec = (size_t)ceil_div(Fc, 32) * 32 * N;     // the step-major arrays are padded to 32 frames
+    *bytes = batch ? (bcjr::beta_floats(Fc, (int)N, S) + 5 * nvec) * sizeof(float) + nvec + 256 : 0;
     return CPB_OK;
 }
 
@@ -1038,7 +1571,8 @@ int cpb_turbo_decode(const cpbTrellis *t, const float *sys_dev, const float *par
     cudaStream_t st = (cudaStream_t)stream;
     const DeviceProps &dp = device_props();
     const int64_t Fc = bcjr::chunk_frames(batch, (int)N, S);
-    const size_t nbeta = bcjr::beta_floats(Fc, (int)N, S), nvec = (size_t)Fc * N;
+    const size_t nbeta = bcjr::beta_floats(Fc, (int)N, S), nvec = (size_t)ceil_div(Fc, 32) * 32 * N;
+    const bool step_major = bcjr::step_major_ok(t, S, (int)N, perm_dev);
     Scratch ws;
     rc = ws.acquire(workspace_dev, workspace_bytes, (nbeta + 5 * nvec) * sizeof(float) + nvec + 256, st);
     if (rc) return rc;
@@ -1051,6 +1585,35 @@ int cpb_turbo_decode(const cpbTrellis *t, const float *sys_dev, const float *par
         const unsigned eg = (unsigned)std::min<int64_t>(ceil_div(tot, 256), (int64_t)dp.sm_count * 32);
         const float *sy = sys_dev + f0 * N, *p1 = par1_dev + f0 * N, *p2 = par2_dev + f0 * N;
         cudaError_t e;
+        if (step_major) {
+            // sys_i = sysT, La1 / La2 = the two extrinsic arrays, L1 / L2 = parity 1 / 2, all (N, pitch); decT = `dec`
+            const int64_t pitch = ceil_div(nb, 32) * 32;
+            float *sysT = sys_i, *p1T = L1, *p2T = L2;
+            const dim3 tg((unsigned)ceil_div(N, 32), (unsigned)(pitch / 32));
+            bcjr::to_step_major_kernel<<<tg, 256, 0, st>>>(sy, nb, (int)N, pitch, sysT);
+            bcjr::to_step_major_kernel<<<tg, 256, 0, st>>>(p1, nb, (int)N, pitch, p1T);
+            bcjr::to_step_major_kernel<<<tg, 256, 0, st>>>(p2, nb, (int)N, pitch, p2T);
+            if (L_int0_dev) { bcjr::to_step_major_kernel<<<tg, 256, 0, st>>>(L_int0_dev + f0 * N, nb, (int)N, pitch, La1); e = cudaGetLastError(); }
+            else e = cudaMemsetAsync(La1, 0, (size_t)N * pitch * sizeof(float), st);                  // turbo.py:304-307
+            if (e == cudaSuccess) e = cudaMemsetAsync(dec, 0, (size_t)N * pitch, st);
+            if (e != cudaSuccess) { rc = record_cuda_error(e, "turbo init", __FILE__, __LINE__); break; }
+            for (int it = 0; it < n_iter && rc == CPB_OK; ++it) {
+                // decoder 1 in natural order (:315); decoder 2 reads the systematic stream and decoder 1's extrinsic through
+                // the interleaver (:310,:318-319) and writes its own extrinsic / decisions back through it (:328-331)
+                rc = bcjr::launch_map(t, S, sysT, p1T, La1, nb, (int)N, noise_variance, 0, beta, La2, nullptr, st, 1, nullptr,
+                                      pitch, nullptr);
+                if (rc) break;
+                const int mode = (it == n_iter - 1) ? 1 : 0;                                            // :320-323
+                rc = bcjr::launch_map(t, S, sysT, p2T, La2, nb, (int)N, noise_variance, mode, beta, La1, dec, st, 1, nullptr,
+                                      pitch, perm_dev);
+            }
+            if (rc) break;
+            const dim3 bg((unsigned)ceil_div(N, 128), (unsigned)(pitch / 32));
+            bcjr::bits_to_frame_major_kernel<<<bg, 256, 0, st>>>(dec, nb, (int)N, pitch, bits_out_dev + f0 * N);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) rc = record_cuda_error(e, "turbo kernels", __FILE__, __LINE__);
+            continue;
+        }
         if (L_int0_dev) e = cudaMemcpyAsync(La1, L_int0_dev + f0 * N, tot * sizeof(float), cudaMemcpyDeviceToDevice, st);
         else e = cudaMemsetAsync(La1, 0, tot * sizeof(float), st);                         // turbo.py:304-307
         if (e == cudaSuccess) e = cudaMemsetAsync(dec, 0, tot, st);

@@ -53,7 +53,7 @@ const DeviceProps &device_props()
     return cache[dev];
 }
 
-int ensure_dyn_smem(const void *kernel, size_t bytes)
+int ensure_dyn_smem(const void *kernel, size_t bytes, bool max_carveout)
 {
     static std::mutex mu;
     static std::unordered_map<unsigned long long, size_t> done;      // (kernel, device) -> largest size opted in
@@ -64,6 +64,11 @@ int ensure_dyn_smem(const void *kernel, size_t bytes)
     auto it = done.find(key);
     if (it != done.end() && it->second >= bytes) return CPB_OK;
     CPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    // kernels that get nothing from L1 ask for the largest shared-memory carve-out: the driver's own choice capped the
+    // step-major MAP kernel at 9 CTAs per SM where its registers allow 12.  (Not for kernels that re-read the other half
+    // of a 32-byte sector from L1, like the frame-major MAP kernel: measured 2x slower with the small L1.)
+    if (max_carveout)
+        CPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     done[key] = bytes;
     return CPB_OK;
 }

@@ -39,7 +39,7 @@ struct Scratch {
 };
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize opt-in, made once per (kernel, device) and size: launches do not pay for it
-int ensure_dyn_smem(const void *kernel, size_t bytes);
+int ensure_dyn_smem(const void *kernel, size_t bytes, bool max_carveout = false);
 
 // explicit test / experiment switches (cpb_set_option); read with relaxed atomics, never from the environment
 int option(int id);

@@ -47,6 +47,10 @@ int cpb_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *global_
 #define CPB_OPT_LDPC_NO_BULK 1            /* 1: min-sum check pass without the bulk-copy staged kernel    */
 #define CPB_OPT_BCJR_WINDOW 2             /* w > 0: MAP windows of w trellis steps (multiple of 8, 128..1024; default 1024): more
                                              parallelism per frame for small batches, 96-step warm-up either side as always */
+#define CPB_OPT_BCJR_PER_STEP_SCALING 3   /* 1: MAP kernel that rescales its metrics every step (the cross-check of the default,
+                                             which rescales every 4th step and falls back per block on decay)          */
+#define CPB_OPT_TURBO_FRAME_MAJOR 4       /* 1: turbo loop on frame-major arrays with separate interleaver kernels (the cross-check
+                                             of the default, which transposes once and indexes rows through the interleaver) */
 #define CPB_OPT_COUNT 8
 int cpb_set_option(int option_id, int value);
 int cpb_get_option(int option_id, int *value);

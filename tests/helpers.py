@@ -193,3 +193,9 @@ def turbo_link_tx_model(trellis, interleaver, frames, frame_bits, seed, first_fr
             z = np.stack([za.real, za.imag, zb.real, zb.imag], axis=1).reshape(-1)[:N]
             ys[fl, j] = (2.0 * np.asarray(streams[j][:N], dtype=np.float64) - 1.0) + noise_sigma * z
     return msg, ys[:, 0], ys[:, 1], ys[:, 2]
+
+
+# (noise variance, amplitude, prior std) of the "contradicted" MAP test frames: random +-amplitude symbols (not code words)
+# plus noise and Gaussian priors.  Branch weights fall to 2^-19 .. 2^-40 per step, so 4-step blocks of map_lin2_kernel decay
+# below its 2^-20 rescaling floor and take the per-step fallback, while every LLR below 40 stays representable in fp32.
+CONTRADICTED_MAP_CASES = ((0.15, 1.0, 6.0), (0.3, 1.5, 8.0), (1.0, 1.0, 1.0))

@@ -68,6 +68,39 @@ def test_map_decode_batch_vs_oracle_long_frames():
         assert (np.abs(L[b] - Lo) <= MAP_ATOL + MAP_RTOL * np.abs(Lo)).all(), float(np.abs(L[b] - Lo).max())
 
 
+def test_map_block_rescaling_matches_per_step_and_oracle_on_contradicted_frames():
+    """The default MAP kernel rescales its metrics every 4th step and redoes a block step by step when the metric sum
+    decays (bcjr.cu, map_lin2_kernel).  Frames whose observations contradict every trellis path (random signs instead of
+    code words, strong random priors) force that fallback -- tests/test_model_map.py counts it on the same cases with the
+    NumPy model of the kernel's arithmetic.  Both kernel forms must agree with the fp64 oracle within the MAP tolerance."""
+    from commpy_b200 import _lib
+    tr = helpers.rsc_k4()
+    rs = np.random.RandomState(77)
+    N, batch = 2048, 40
+    for s2, amp, lamp in helpers.CONTRADICTED_MAP_CASES:
+        ys = amp * rs.choice([-1.0, 1.0], (batch, N)) + np.sqrt(s2) * rs.randn(batch, N)
+        yp = amp * rs.choice([-1.0, 1.0], (batch, N)) + np.sqrt(s2) * rs.randn(batch, N)
+        La = lamp * rs.randn(batch, N)
+        res = {}
+        for per_step in (1, 0):
+            _lib.set_option(_lib.OPT_BCJR_PER_STEP_SCALING, per_step)
+            try:
+                L, bits = map_decode_batch(ys, yp, tr, s2, La, "decode")
+            finally:
+                _lib.set_option(_lib.OPT_BCJR_PER_STEP_SCALING, 0)
+            res[per_step] = (L.cpu().numpy().astype(np.float64), bits.cpu().numpy())
+        assert np.isfinite(res[0][0]).all()
+        for b in range(0, batch, 8):
+            Lo, bo = oracle.map_decode(ys[b], yp[b], tr, s2, La[b], "decode")
+            ok = np.isfinite(Lo) & (np.abs(Lo) < 40.0)
+            assert ok.mean() > 0.9
+            for k in (0, 1):
+                d = np.abs(res[k][0][b][ok] - Lo[ok])
+                assert (d <= MAP_ATOL + MAP_RTOL * np.abs(Lo[ok])).all(), (k, s2, float(d.max()))
+                big = ok & (np.abs(Lo) > 1e-2)
+                assert np.array_equal(res[k][1][b][big], bo[big])
+
+
 def test_turbo_decode_golden_and_batch():
     g = np.load(os.path.join(GOLD, "bcjr_turbo.npz"))
     tr = helpers.rsc_k4()
