@@ -392,7 +392,7 @@ class TurboWorkload(Workload):
         g.manual_seed(2000 + rank)
         self.y = [(-1 + self.s2 ** 0.5 * torch.randn(self.batch, self.N, device="cuda", generator=g)).float() for _ in range(3)]
         self.zero = torch.zeros((self.batch, self.N), dtype=torch.uint8, device="cuda")
-        self.kernel_launches_per_step = 4 * self.iters + 2
+        self.kernel_launches_per_step = 2 * self.iters + 5      # 3 transposes in, 2 MAP passes per iteration, decisions out, error count
 
     def step(self, torch, counters, ev=None):
         from commpy_b200.channelcoding import turbo_decode_batch

@@ -2,11 +2,13 @@
 
 Mirror of commpy/channelcoding/turbo.py.  `map_decode` / `turbo_decode` run in CUDA
 (commpy_b200/csrc/bcjr.cu) through `cpb_map_decode[_host]` / `cpb_turbo_decode[_host]`; there is no CPU decode path.
-The hot kernel works, like the reference, with probabilities renormalised every step (float32 instead of float64,
-branch weights taken relative to the step's best symbol so nothing underflows); one thread owns a window of 1024
-trellis steps of a frame and warms its recursions up over 96 steps of the neighbouring windows (<= 3.4e-7 on the LLRs
-against the reference's full-frame recursion).  Unaligned frame lengths and other trellises take the log-domain exact
-max* kernels.  LLRs agree to ~1e-5 where the reference is finite (it returns +-inf once its exponentials underflow; the
+The hot kernel works, like the reference, with renormalised probabilities (float32 instead of float64, branch weights
+taken relative to the step's most likely (input, parity) pair so nothing overflows; rescaled every 4th step, a block
+whose metric sum decays is redone with the reference's per-step rescaling); one thread owns a window of 1024 trellis
+steps of a frame and warms its recursions up over 96 steps of the neighbouring windows (<= 3.4e-7 on the LLRs against
+the reference's full-frame recursion).  `turbo_decode` transposes the symbol streams to step-major once, so the
+interleaver is a row index of the MAP kernel instead of a data movement.  Unaligned frame lengths and other trellises
+take the log-domain exact max* kernels.  LLRs agree to ~1e-5 where the reference is finite (it returns +-inf once its exponentials underflow; the
 GPU path stays finite there).
 """
 import ctypes as C

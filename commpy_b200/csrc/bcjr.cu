@@ -2,13 +2,18 @@
 // (_backward_recursion), :114-158 (_forward_recursion_decoding), :163-251 (map_decode) and the iteration
 // loop of :254-333 (turbo_decode).
 //
-// Kernel families (all compute the exact log-MAP of the reference, float32 instead of float64):
-//   tpf::map_lin_kernel<T>   the hot one (aligned frames, compile-time trellis T): PROBABILITY domain like the reference
-//                            itself (renormalised every step, turbo.py:106-111,155), branch weights relative to the
-//                            step's best symbol (all <= 1: nothing underflows), one THREAD per (frame, window of 1024
-//                            steps) with a 96-step warm-up of alpha and beta over the neighbouring windows, beta
-//                            checkpointed every 8 steps in a global scratch and recomputed per segment in shared memory;
-//                            in the turbo loop it writes the extrinsic L - L_int itself.
+// Kernel families (all compute the exact MAP of the reference, float32 instead of float64):
+//   tpf::map_lin2_kernel<T,SM> the hot one (systematic compile-time trellis T, frame length a multiple of 4): PROBABILITY
+//                            domain like the reference itself, one THREAD per (frame, window of 1024 steps) with a 96-step
+//                            warm-up of alpha and beta over the neighbouring windows; four branch weights per step relative
+//                            to the most likely (input, parity) pair; metrics rescaled every 4th step (the reference
+//                            rescales every step, turbo.py:106-111,155 -- a block whose sum decays is redone per step); beta
+//                            checkpointed every 8 steps in a global scratch and recomputed per segment in shared memory; in
+//                            the turbo loop it writes the extrinsic L - L_int itself.  SM = step-major arrays
+//                            [step][frame]: inputs staged by cp.async, the interleaver is a row index (turbo loop);
+//                            otherwise frame-major rows read as 16-byte vectors (map_decode).
+//   tpf::map_lin_kernel<T>   the same with per-step rescaling and separate prior / channel weights (non-systematic
+//                            compile-time trellises; cross-check of map_lin2 behind CPB_OPT_BCJR_PER_STEP_SCALING).
 //   tpf::map_ckpt_kernel /   log2-domain exact max* forms of the same thread mapping (unaligned lengths; compile-time
 //   tpf::map_tpf_kernel      switch CPB_BCJR_LOGDOMAIN).
 //   map_kernel<S>            table-driven fallback for any other rate-1/2 trellis with <= 32 states: one LANE per state,
@@ -20,7 +25,9 @@
 //   alpha_t(ns)   = max*    alpha_{t-1}(s)  + gamma_t(s,u) + u*La_t             :136-138, alpha_0 = delta(s,0)
 //   L_t = La_t + max*_s[alpha_{t-1}(s)+gamma_t(s,1)+beta_t(ns(s,1))] - max*_s[... u = 0 ...]     :141-146
 // (log P(u) = u*La - softplus(La); the common term cancels like the reference's normalisations do).
-// The turbo loop (cpb_turbo_decode) is 2 MAP launches + 2 row-staged interleaver launches per iteration.
+// The turbo loop (cpb_turbo_decode) transposes the three symbol streams to step-major once and then runs 2 MAP launches per
+// iteration -- decoder 2 addresses rows through the interleaver, so no data is permuted; on trellises / lengths the
+// step-major kernel does not take it is 2 MAP launches + 2 row-staged interleaver launches per iteration on frame-major rows.
 #include <algorithm>
 
 #include <cstdlib>
@@ -783,7 +790,8 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
     constexpr int SV = S / 4;                   // float4 words per metric vector
     static_assert(S % 4 == 0 && systematic<T>(), "systematic trellis with 4 or 8 states");
     extern __shared__ float4 smem_v[];
-    const int tid = threadIdx.x, bd = blockDim.x;
+    constexpr int bd = 32;                      // one warp per CTA (launch<T>): every shared-memory offset is an immediate
+    const int tid = threadIdx.x;
     float4 *sb = smem_v;                        // [CK][SV][bd]  beta of the current segment
     float4 *sg = smem_v + CK * SV * bd;         // [CK][bd]      the four branch weights of a step
     float *sl = reinterpret_cast<float *>(sg + CK * bd);   // [CK][bd]  L_int of a step
@@ -797,12 +805,15 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
     const float *fs = p.sys + f * N, *fp = p.par + f * N, *fl = p.La + f * N;
     float *ck = p.beta + g;
     const float c2 = 2.0f * p.c;
+    const uint32_t NT32 = (uint32_t)p.NT;       // checkpoint (segment j, state s) at ck[(j S + s) NT]: 32-bit offsets (launch_map checks)
 
     // weights of the four (u, cp) pairs relative to the most likely pair: index o = u << 1 | cp
     auto weights = [&](float ys, float yp, float la_raw) -> float4 {
+        // (no clamp on the channel terms: ex2 of a large negative number is 0, an infinite symbol gives weights (1, 0),
+        // and the clamped prior keeps infinity - infinity out)
         const float l = fminf(fmaxf(la_raw * LOG2E, -60.0f), 60.0f);
-        const float lu = fminf(fmaxf(ys * c2, -120.0f), 120.0f) + l;       // log2 odds of u = 1: channel + prior
-        const float lb = fminf(fmaxf(yp * c2, -120.0f), 120.0f);           // log2 odds of cp = 1
+        const float lu = fmaf(ys, c2, l);                                  // log2 odds of u = 1: channel + prior
+        const float lb = yp * c2;                                          // log2 odds of cp = 1
         const float eu = ex2(-fabsf(lu)), eb = ex2(-fabsf(lb));
         const float u1 = (lu >= 0.0f) ? 1.0f : eu, u0 = (lu >= 0.0f) ? eu : 1.0f;
         const float q1 = (lb >= 0.0f) ? 1.0f : eb, q0 = (lb >= 0.0f) ? eb : 1.0f;
@@ -875,13 +886,17 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
     auto rows_of = [&](int e0) -> int4 {                               // rows of elements e0 .. e0+3
         return p.rmap ? __ldg(reinterpret_cast<const int4 *>(p.rmap + e0)) : make_int4(e0, e0 + 1, e0 + 2, e0 + 3);
     };
+    // element (row, frame) of a step-major array sits at row * pitch + frame: 32-bit offsets (launch_map checks N * pitch)
+    const uint32_t pitch32 = (uint32_t)p.pitch, f32 = (uint32_t)f;
     auto issue_group = [&](uint32_t dst, int e0, const int4 &r) {      // 12 floats -> dst + 4 bd k
         const int rr[G] = {r.x, r.y, r.z, r.w};
+        const uint32_t op = (uint32_t)e0 * pitch32 + f32;
 #pragma unroll
         for (int i = 0; i < G; ++i) {
-            cp4(dst + 4u * bd * i, p.sys + (int64_t)rr[i] * p.pitch + f);
-            cp4(dst + 4u * bd * (4 + i), p.par + (int64_t)(e0 + i) * p.pitch + f);
-            cp4(dst + 4u * bd * (8 + i), p.La + (int64_t)rr[i] * p.pitch + f);
+            const uint32_t o = (uint32_t)rr[i] * pitch32 + f32;
+            cp4(dst + 4u * bd * i, p.sys + o);
+            cp4(dst + 4u * bd * (4 + i), p.par + (op + (uint32_t)i * pitch32));
+            cp4(dst + 4u * bd * (8 + i), p.La + o);
         }
     };
     // a stream of `ng` groups, group n = elements first + n * stride .. +3, through the ring: start() fills the ring,
@@ -950,7 +965,7 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
                 if (e1 <= hi && (((e1 - lo) % CK) == 0 || e1 == hi)) {        // beta_{e1}: the checkpoint of segment j
                     const int j = (e1 - lo + CK - 1) / CK - 1;
 #pragma unroll
-                    for (int s = 0; s < S; ++s) ck[((int64_t)j * S + s) * p.NT] = B[s];
+                    for (int s = 0; s < S; ++s) (ck + (uint32_t)(j * S) * NT32)[(uint32_t)s * NT32] = B[s];
                 }
                 beta_block(B, gw);
             }
@@ -966,7 +981,7 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
             if (e1 <= hi && (((e1 - lo) % CK) == 0 || e1 == hi)) {        // beta_{e1}: the checkpoint of segment j
                 const int j = (e1 - lo + CK - 1) / CK - 1;
 #pragma unroll
-                for (int s = 0; s < S; ++s) ck[((int64_t)j * S + s) * p.NT] = B[s];
+                for (int s = 0; s < S; ++s) (ck + (uint32_t)(j * S) * NT32)[(uint32_t)s * NT32] = B[s];
             }
             beta_block(B, gw);
         };
@@ -983,7 +998,8 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
 #pragma unroll
     for (int s = 0; s < S; ++s) A[s] = (ta == 0) ? ((s == 0) ? 1.0f : 0.0f) : (1.0f / S);    // alpha_0 = delta(s,0), :220-221
     // one alpha step; with EMIT the a-posteriori log2 ratio of the step (prior included) from the beta words bt[0..SV)
-    auto alpha_raw = [&](float (&A_)[S], const float4 &gw, const float4 *bt, bool emit, float &D) {
+    bool small = false;
+    auto alpha_raw = [&](float (&A_)[S], const float4 &gw, const float4 *bt, bool emit, float &D, bool rescue = false) {
         float tx[2 * S];
 #pragma unroll
         for (int e = 0; e < 2 * S; ++e) tx[e] = A_[e >> 1] * pick(gw, T::out(e >> 1, e & 1));
@@ -1000,7 +1016,9 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
                 a0 += tx[2 * s] * bv[T::ns(s, 0)];
                 a1 += tx[2 * s + 1] * bv[T::ns(s, 1)];
             }
-            if (fmaxf(a0, a1) < 9.094947017729282e-13f) {     // both below 2^-40 (contradicted observations): redo the sums 2^80 up
+            // both sums below 2^-40 (contradicted observations): the block is redone with `rescue`, which takes the sums 2^80 up
+            small = small || (fmaxf(a0, a1) < 9.094947017729282e-13f);
+            if (rescue && fmaxf(a0, a1) < 9.094947017729282e-13f) {
                 a0 = a1 = 0.0f;
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
@@ -1021,7 +1039,7 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
         for (int h = 0; h < 2; ++h)
             if (h * G < ns) issue_group(seg_s + 4u * bd * 12 * h, s0 + h * G, rows_of(s0 + h * G));
 #pragma unroll
-        for (int s = 0; s < S; ++s) cp4(seg_s + 4u * bd * (24 + s), ck + ((int64_t)j * S + s) * p.NT);
+        for (int s = 0; s < S; ++s) cp4(seg_s + 4u * bd * (24 + s), (ck + (uint32_t)(j * S) * NT32) + (uint32_t)s * NT32);
         commit();
     };
     if constexpr (SM) {
@@ -1065,7 +1083,7 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
         for (int h = 0; h < 2; ++h)
             if (h * G < ns) ld3(s0 + h * G, xi[h][0], xi[h][1], xi[h][2]);
 #pragma unroll
-        for (int s = 0; s < S; ++s) xc[s] = ck[((int64_t)j * S + s) * p.NT];
+        for (int s = 0; s < S; ++s) xc[s] = (ck + (uint32_t)(j * S) * NT32)[(uint32_t)s * NT32];
     };
     if constexpr (!SM) {
 #pragma unroll
@@ -1143,15 +1161,16 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
             float A0[S], Dv[G];
 #pragma unroll
             for (int s = 0; s < S; ++s) A0[s] = A[s];
+            small = false;
 #pragma unroll
             for (int i = 0; i < G; ++i) alpha_raw(A, sg[(h * G + i) * bd + tid], sb + (h * G + i) * SV * bd + tid, true, Dv[i]);
             float sum = total(A);
-            if (!(sum >= RESCALE_FLOOR)) {
+            if (!(sum >= RESCALE_FLOOR) || small) {
 #pragma unroll
                 for (int s = 0; s < S; ++s) A[s] = A0[s];
 #pragma unroll
                 for (int i = 0; i < G; ++i) {
-                    alpha_raw(A, sg[(h * G + i) * bd + tid], sb + (h * G + i) * SV * bd + tid, true, Dv[i]);
+                    alpha_raw(A, sg[(h * G + i) * bd + tid], sb + (h * G + i) * SV * bd + tid, true, Dv[i], true);
                     scale(A, total(A));
                 }
                 sum = total(A);
@@ -1170,8 +1189,9 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
                 rows4(e0, r);
 #pragma unroll
                 for (int i = 0; i < G; ++i) {
-                    p.L_out[(int64_t)r[i] * p.pitch + f] = p.ext ? Le[i] : Lv[i];
-                    if (p.bits_out) p.bits_out[(int64_t)r[i] * p.pitch + f] = (uint8_t)(p.mode == 1 && Lv[i] > 0.0f);
+                    const uint32_t o = (uint32_t)r[i] * pitch32 + f32;
+                    p.L_out[o] = p.ext ? Le[i] : Lv[i];
+                    if (p.bits_out) p.bits_out[o] = (uint8_t)(p.mode == 1 && Lv[i] > 0.0f);
                 }
             } else {
                 if (p.ext) *reinterpret_cast<float4 *>(p.L_out + f * N + e0) = make_float4(Le[0], Le[1], Le[2], Le[3]);
@@ -1231,7 +1251,8 @@ static int launch(const Params &p, bool vec, cudaStream_t st)
         map_ckpt_kernel<T><<<grid, bd, smem, st>>>(p);
 #else
         if constexpr (systematic<T>() && T::S % 4 == 0) {
-            if (!option(CPB_OPT_BCJR_PER_STEP_SCALING)) {
+            // (the kernel indexes its checkpoints with 32-bit offsets: always true for the chunks chunk_frames() makes)
+            if (!option(CPB_OPT_BCJR_PER_STEP_SCALING) && p.NT * (int64_t)(ceil_div(p.win, CK) * T::S) < (1ll << 31)) {
                 // beta, weights and L_int of a segment; step-major: + the 32 staged floats of the next segment (the beta /
                 // weight area doubles as the input ring of the backward sweep)
                 const size_t smem2 = (size_t)bd * (CK * (T::S / 4 * sizeof(float4) + sizeof(float4) + sizeof(float)) +
@@ -1444,6 +1465,7 @@ static int launch_map(const cpbTrellis *t, int S, const float *sys, const float 
         if (want_ext && vec && (p.win % tpf::CK) == 0) p.ext = 1;
 #endif
         if (pitch && !(vec && (p.win % tpf::CK) == 0 && p.ext)) return CPB_EINVAL;      // step_major_ok() said otherwise
+        if (pitch && (int64_t)N * pitch >= (1ll << 31)) return CPB_EINVAL;              // 32-bit element offsets in the kernel
         if (did_ext) *did_ext = p.ext;
         if (tpf::matches<tpf::RscK4>(hn, ho, S)) return tpf::launch<tpf::RscK4>(p, vec, st);
         if (tpf::matches<tpf::RscK4Legacy>(hn, ho, S)) return tpf::launch<tpf::RscK4Legacy>(p, vec, st);

@@ -1,11 +1,10 @@
 #!/bin/bash
-# one gpurun call: turbo timing for the kernel / layout switches, the MAP / turbo / link parity tests, and full ncu captures
-# of the two MAP launches of one turbo iteration
+# one gpurun call: turbo timing for the kernel / layout switches, the whole GPU test suite, and full ncu captures of the two
+# MAP launches of one turbo iteration
 mkdir -p gpurun_out
 python scripts/exp_map.py > gpurun_out/exp_map.log 2>&1
-for v in build/variants/libcommpy_b200_*.so; do [ -f $v ] && COMMPY_B200_LIB=$PWD/$v python scripts/exp_map.py >> gpurun_out/exp_map.log 2>&1; done
 cat gpurun_out/exp_map.log
-timeout 600 python -m pytest tests/test_decoders_gpu.py tests/test_links.py -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:map_lin2 -c 2 -o gpurun_out/r02_map_lin2 -f \
     python scripts/profile_decoders.py turbo > gpurun_out/ncu_map.log 2>&1
 tail -3 gpurun_out/ncu_map.log
