@@ -820,11 +820,15 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
         return make_float4(u0 * q0, u0 * q1, u1 * q0, u1 * q1);
     };
     auto pick = [](const float4 &v, int o) -> float { return o == 0 ? v.x : (o == 1 ? v.y : (o == 2 ? v.z : v.w)); };
-    auto total = [](const float (&v)[S]) {
-        float sum = v[0];
+    auto total = [](const float (&v)[S]) {              // pairwise: three dependent adds instead of seven
+        float t[S];
 #pragma unroll
-        for (int s = 1; s < S; ++s) sum += v[s];
-        return sum;
+        for (int s = 0; s < S; ++s) t[s] = v[s];
+#pragma unroll
+        for (int w = S / 2; w >= 1; w >>= 1)
+#pragma unroll
+            for (int s = 0; s < w; ++s) t[s] += t[s + w];
+        return t[0];
     };
     auto scale = [](float (&v)[S], float sum) {
         const float r = rcp(fmaxf(sum, 1.0e-37f));
@@ -915,10 +919,11 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
         const float *q = ring + slot * 12 * bd + tid;
 #pragma unroll
         for (int i = 0; i < G; ++i) { vs[i] = q[i * bd]; vp[i] = q[(4 + i) * bd]; vl[i] = q[(8 + i) * bd]; }
-        if (n + RB < ng) {
-            issue_group(ring_s + 4u * bd * 12 * slot, first + (n + RB) * stride, rnext);
-            if (n + RB + 1 < ng) rnext = rows_of(first + (n + RB + 1) * stride);
-        }
+        // (the interleaver entries of the group after next are requested BEFORE this group's copies: behind twelve DRAM
+        // misses in the load queue they came back too late -- 12 % of decoder 2's warp samples waited on them)
+        const int4 rcur = rnext;
+        if (n + RB + 1 < ng) rnext = rows_of(first + (n + RB + 1) * stride);
+        if (n + RB < ng) issue_group(ring_s + 4u * bd * 12 * slot, first + (n + RB) * stride, rcur);
         commit();
     };
     // four beta steps (newest first: gw[3] is the latest step), rescaled at the end; the per-step form if they decayed
@@ -1010,12 +1015,15 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
                 const float4 q = bt[v * bd];
                 bv[4 * v] = q.x; bv[4 * v + 1] = q.y; bv[4 * v + 2] = q.z; bv[4 * v + 3] = q.w;
             }
-            float a0 = 0.0f, a1 = 0.0f;
+            float a0 = 0.0f, a1 = 0.0f, c0 = 0.0f, c1 = 0.0f;       // two partial sums each: shorter dependency chains
 #pragma unroll
-            for (int s = 0; s < S; ++s) {
+            for (int s = 0; s < S; s += 2) {
                 a0 += tx[2 * s] * bv[T::ns(s, 0)];
                 a1 += tx[2 * s + 1] * bv[T::ns(s, 1)];
+                c0 += tx[2 * s + 2] * bv[T::ns(s + 1, 0)];
+                c1 += tx[2 * s + 3] * bv[T::ns(s + 1, 1)];
             }
+            a0 += c0; a1 += c1;
             // both sums below 2^-40 (contradicted observations): the block is redone with `rescue`, which takes the sums 2^80 up
             small = small || (fmaxf(a0, a1) < 9.094947017729282e-13f);
             if (rescue && fmaxf(a0, a1) < 9.094947017729282e-13f) {
@@ -1033,18 +1041,27 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
     };
     // step-major: the first segment's inputs and checkpoint are requested before the warm-up, segment j+1's when segment j
     // has been read out of `segbuf` (32 floats: 2 x 12 inputs, 8 checkpoint values)
-    auto issue_segment = [&](int s0, int j) {
+    int4 rc[2], rn[2];                          // rows of the current / the next segment (the interleaver entries are
+                                                // loaded a segment before the addresses they form are needed)
+    rc[0] = rc[1] = rn[0] = rn[1] = make_int4(0, 0, 0, 0);
+    auto segment_rows = [&](int s0, int4 (&r)[2]) {
         const int ns = min(CK, hi - s0);
 #pragma unroll
         for (int h = 0; h < 2; ++h)
-            if (h * G < ns) issue_group(seg_s + 4u * bd * 12 * h, s0 + h * G, rows_of(s0 + h * G));
+            if (h * G < ns) r[h] = rows_of(s0 + h * G);
+    };
+    auto issue_segment = [&](int s0, int j, const int4 (&r)[2]) {
+        const int ns = min(CK, hi - s0);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (h * G < ns) issue_group(seg_s + 4u * bd * 12 * h, s0 + h * G, r[h]);
 #pragma unroll
         for (int s = 0; s < S; ++s) cp4(seg_s + 4u * bd * (24 + s), (ck + (uint32_t)(j * S) * NT32) + (uint32_t)s * NT32);
         commit();
     };
     if constexpr (SM) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");   // (only empty groups are pending: the ring's slots are free)
-        if (lo < hi) issue_segment(lo, 0);
+        if (lo < hi) { segment_rows(lo, rn); issue_segment(lo, 0, rn); }
         stream_start(ta, G, (lo - ta) / G);
     }
     int wslot = 0;
@@ -1093,6 +1110,8 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
     for (int s0 = lo, j = 0; s0 < hi; s0 += CK, ++j) {
         const int ns = min(CK, hi - s0);                        // 4 or 8
         if constexpr (SM) {
+            rc[0] = rn[0]; rc[1] = rn[1];
+            if (s0 + CK < hi) segment_rows(s0 + CK, rn);
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             const float *q = segbuf + tid;
 #pragma unroll
@@ -1118,7 +1137,7 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
 #pragma unroll
         for (int s = 0; s < S; ++s) B[s] = xck[0][s];
         if constexpr (SM) {
-            if (s0 + CK < hi) issue_segment(s0 + CK, j + 1);
+            if (s0 + CK < hi) issue_segment(s0 + CK, j + 1, rn);
         } else {
 #pragma unroll
             for (int k = 0; k + 1 < PFF; ++k) {
@@ -1142,8 +1161,11 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
             float B0[S];
 #pragma unroll
             for (int s = 0; s < S; ++s) B0[s] = B[s];
+            float4 gq[G];                                        // (read before the stores below, which the compiler must
+#pragma unroll                                                   //  assume to alias them)
+            for (int i = 0; i < G; ++i) gq[i] = sg[(h * G + i) * bd + tid];
 #pragma unroll
-            for (int i = G - 1; i >= 0; --i) { store_beta(h * G + i, B); beta_raw(B, sg[(h * G + i) * bd + tid]); }
+            for (int i = G - 1; i >= 0; --i) { store_beta(h * G + i, B); beta_raw(B, gq[i]); }
             float sum = total(B);
             if (!(sum >= RESCALE_FLOOR)) {
 #pragma unroll
@@ -1162,8 +1184,11 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
 #pragma unroll
             for (int s = 0; s < S; ++s) A0[s] = A[s];
             small = false;
+            float4 gq[G];
 #pragma unroll
-            for (int i = 0; i < G; ++i) alpha_raw(A, sg[(h * G + i) * bd + tid], sb + (h * G + i) * SV * bd + tid, true, Dv[i]);
+            for (int i = 0; i < G; ++i) gq[i] = sg[(h * G + i) * bd + tid];
+#pragma unroll
+            for (int i = 0; i < G; ++i) alpha_raw(A, gq[i], sb + (h * G + i) * SV * bd + tid, true, Dv[i]);
             float sum = total(A);
             if (!(sum >= RESCALE_FLOOR) || small) {
 #pragma unroll
@@ -1185,8 +1210,8 @@ __global__ void __launch_bounds__(32, CPB_MAP_MINB) map_lin2_kernel(const Params
             }
             const int e0 = s0 + h * G;
             if (SM) {
-                int r[G];
-                rows4(e0, r);
+                const int4 rr = (h == 0) ? rc[0] : rc[1];
+                const int r[G] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
                 for (int i = 0; i < G; ++i) {
                     const uint32_t o = (uint32_t)r[i] * pitch32 + f32;

@@ -82,7 +82,32 @@ int Scratch::acquire(void *user, size_t user_bytes, size_t need, cudaStream_t s)
         ptr = user; owned = false;
         return CPB_OK;
     }
-    CPB_CUDA(cudaMallocAsync(&ptr, need, s));
+    // the library's own stream-ordered pool (one per device), which keeps what it has been given: with the default pool's
+    // release threshold of 0 every synchronisation returned the scratch to the driver and the next call paid for gigabytes
+    // of fresh physical memory (the host-buffer pipelines synchronise once per call)
+    static std::mutex mu;
+    static std::unordered_map<int, cudaMemPool_t> pools;
+    int dev = 0;
+    CPB_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t pool = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = pools.find(dev);
+        if (it == pools.end()) {
+            cudaMemPoolProps props{};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            CPB_CUDA(cudaMemPoolCreate(&pool, &props));
+            uint64_t keep = UINT64_MAX;
+            CPB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            pools[dev] = pool;
+        } else {
+            pool = it->second;
+        }
+    }
+    CPB_CUDA(cudaMallocFromPoolAsync(&ptr, need, pool, s));
     owned = true;
     return CPB_OK;
 }

@@ -22,7 +22,7 @@ s2 = 1.0 / (2 * (1 / 3) * 10 ** (1.0 / 10))
 modes = [("per-step, frame-major", 1, 1), ("block, frame-major", 0, 1), ("block, step-major", 0, 0)]
 if not os.environ.get("EXP_REF"):
     modes = modes[1:]
-for batch, wins in ((8192, (0,)), (4096, (0, 512)), (1024, (128, 192))):
+for batch, wins in ((8192, (0,)), (1024, (128,))):
     g = torch.Generator(device="cuda"); g.manual_seed(5)
     y = [(-1 + s2 ** 0.5 * torch.randn(batch, N, device="cuda", generator=g)).float() for _ in range(3)]
     for win in wins:
