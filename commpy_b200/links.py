@@ -314,7 +314,7 @@ class ConvLinkGPU:
         _lib.check(rc, "count_errors")
         return dec
 
-    def link_performance(self, SNRs, send_max, err_min, return_counters=False, stop_early=True):
+    def link_performance(self, SNRs, send_max, err_min, return_counters=False, stop_early=True, overlap_points=True):
         """BER per SNR (dB, `SNR = Eb/N0 + 10 log10(bits/symbol)` as in the reference's examples,
         conv_encode_decode.py:102; the code rate enters through `set_SNR_dB`, channels.py:74).  A point ends
         when the GLOBAL counters reach `err_min` errors or `send_max` bits; like the reference the sweep stops after
@@ -326,18 +326,33 @@ class ConvLinkGPU:
         error threshold was crossed is discarded, so the counters are exactly those of the in-order rule.
         With return_counters=True also returns the summed [bit errors, frame errors, bits] tensor of all points.
         stop_early=False measures every point of the sweep (the reference abandons the sweep after the first point that
-        ends below err_min errors)."""
+        ends below err_min errors).
+        The counters of a point's LAST batch are read after the next point's first batch has been issued (that batch is
+        discarded if the sweep ends there), so the GPU does not idle between points either; overlap_points=False reads them
+        at once -- same BERs and counters, the cross-check of the test suite."""
         torch = _lib.require_cuda()
         BERs = np.zeros(len(SNRs))
         batch_index = 0
         _, world, _ = parallel.world()
         bits_per_batch = self.frames * max(world, 1) * self.frame_bits
         grand = torch.zeros(3, dtype=torch.int64, device="cuda")
+        pinned = torch.empty((8, 3), dtype=torch.int64).pin_memory()       # snapshot slots: at most 3 are in flight
+        nslot = 0
+        deferred = None                # (point, snapshot) of a point whose LAST batch is still running
+        stopped = False
+
+        def close(point, entry):
+            """take a finished point's counters; True if the sweep ends here (links.py:339-341)"""
+            entry[2].synchronize()
+            c = entry[1].numpy()
+            grand.add_(entry[0])
+            BERs[point] = c[0] / c[2]
+            return bool(stop_early and c[0] < err_min)
+
         for i, snr in enumerate(SNRs):
             tot = torch.zeros(3, dtype=torch.int64, device="cuda")          # bit errors, frame errors, bits sent
             hist = []                                                        # (device snapshot, pinned copy, event)
             bits_known = 0
-            chosen = None
             while True:
                 msg, y, nv = self.make_batch(float(snr), batch_index, torch)
                 batch_index += 1
@@ -346,26 +361,37 @@ class ConvLinkGPU:
                 local[2] = msg.numel()
                 parallel.allreduce_counters(local)
                 tot = tot + local
-                host = torch.empty(3, dtype=torch.int64).pin_memory()
+                host = pinned[nslot]
+                nslot = (nslot + 1) % pinned.shape[0]
                 host.copy_(tot, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record()
                 hist.append((tot, host, ev))
                 bits_known += bits_per_batch
+                if deferred is not None:
+                    # the previous point's last batch ran while this point's first batch was being issued: the GPU never
+                    # waits for the host between points (this batch is discarded if the sweep ends at that point)
+                    point, entry = deferred
+                    deferred = None
+                    if close(point, entry):
+                        stopped = True
+                        break
                 if len(hist) >= 2:                                           # batch b-1, while batch b runs
                     hist[-2][2].synchronize()
                     if int(hist[-2][1][0]) >= err_min:
-                        chosen = hist[-2]
+                        if close(i, hist[-2]):
+                            stopped = True
                         break
                 if bits_known >= send_max:
-                    hist[-1][2].synchronize()
-                    chosen = hist[-1]
+                    if overlap_points:
+                        deferred = (i, hist[-1])
+                    elif close(i, hist[-1]):
+                        stopped = True
                     break
-            c = chosen[1].numpy()
-            grand += chosen[0]
-            BERs[i] = c[0] / c[2]
-            if stop_early and c[0] < err_min:
+            if stopped:
                 break
+        if deferred is not None and not stopped:
+            close(*deferred)
         if return_counters:
             return BERs, grand
         return BERs

@@ -118,6 +118,29 @@ def test_conv_link_gpu_qpsk_k7_soft_ber_and_oracle_agreement():
     assert int(cnt[0]) == int((dec != msg.cpu().numpy()).sum())
 
 
+@pytest.mark.gpu
+def test_link_performance_point_overlap_changes_nothing():
+    """ConvLinkGPU.link_performance reads a point's last counters after the next point's first batch has been issued
+    (overlap_points=True, the default): BERs and counters equal the read-at-once order, for single- and multi-batch points,
+    with the reference's early end of the sweep (links.py:339-341) and without it."""
+    from commpy_b200.modulation import QAMModem
+    tr = helpers.k7()
+    snr = np.array([1.0, 2.5, 4.0, 7.0, 9.0]) + 10 * math.log10(2)
+    for frames, send_max, err_min, stop_early in ((256, 2e5, 300, True), (256, 1.2e6, 2000, True), (128, 3e5, 10 ** 9, False),
+                                                  (256, 6e5, 150, False)):
+        res = []
+        for overlap in (False, True):
+            link = ConvLinkGPU(tr, QAMModem(4), frame_bits=1024, frames_per_batch=frames, decoding_type="soft", seed=9)
+            bers, cnt = link.link_performance(snr, send_max=send_max, err_min=err_min, return_counters=True,
+                                              stop_early=stop_early, overlap_points=overlap)
+            res.append((bers, cnt.cpu().numpy()))
+        assert np.array_equal(res[0][0], res[1][0]), (frames, send_max, err_min, res)
+        assert np.array_equal(res[0][1], res[1][1])
+        assert res[0][0][0] > 0
+        if stop_early:
+            assert res[0][0][-1] == 0.0            # the sweep ended before the last point, which stays unfilled
+
+
 def test_philox_model_known_answers():
     """The NumPy Philox4x32-10 the TX-chain test is built on reproduces the Random123 known-answer vectors."""
     r = helpers.philox4x32_10(np.array([[0, 0, 0, 0]], dtype=np.uint64), (0, 0))[0]
