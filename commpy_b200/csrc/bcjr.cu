@@ -1265,7 +1265,7 @@ template <class T>
 static int launch(const Params &p, bool vec, cudaStream_t st)
 {
     unsigned grid = (unsigned)ceil_div(p.NT, 128);
-    if (vec && (p.win % CK) == 0) {
+    if (vec && (p.win % 4) == 0) {          // (a window that is not a multiple of CK ends in a 4-step segment)
         // one warp per CTA: 49,152 threads (C3: 8,192 frames x 6 windows) are 1,536 CTAs instead of 384, which
         // spreads evenly over 148 SMs (measured 0.88 vs 0.91 ms per pass)
         const int bd = 32;
@@ -1487,9 +1487,9 @@ static int launch_map(const cpbTrellis *t, int S, const float *sys, const float 
         p.ext = 0;
         p.pitch = pitch; p.rmap = rmap;
 #ifndef CPB_BCJR_LOGDOMAIN
-        if (want_ext && vec && (p.win % tpf::CK) == 0) p.ext = 1;
+        if (want_ext && vec && (p.win % 4) == 0) p.ext = 1;
 #endif
-        if (pitch && !(vec && (p.win % tpf::CK) == 0 && p.ext)) return CPB_EINVAL;      // step_major_ok() said otherwise
+        if (pitch && !(vec && (p.win % 4) == 0 && p.ext)) return CPB_EINVAL;      // step_major_ok() said otherwise
         if (pitch && (int64_t)N * pitch >= (1ll << 31)) return CPB_EINVAL;              // 32-bit element offsets in the kernel
         if (did_ext) *did_ext = p.ext;
         if (tpf::matches<tpf::RscK4>(hn, ho, S)) return tpf::launch<tpf::RscK4>(p, vec, st);
@@ -1535,7 +1535,7 @@ static bool step_major_ok(const cpbTrellis *t, int S, int N, const int32_t *perm
     if (N % 4 != 0 || (reinterpret_cast<uintptr_t>(perm_dev) & 15) != 0) return false;
     const int nwin = tpf::nwindows(N);
     const int win = (nwin == 1) ? N : tpf::window_len();
-    if (win % tpf::CK != 0) return false;
+    if (win % 4 != 0) return false;
     const int32_t *hn = nullptr, *ho = nullptr;
     cpb_trellis_host_tables(t, &hn, &ho);
     return (tpf::matches<tpf::RscK4>(hn, ho, S) && tpf::systematic<tpf::RscK4>()) ||

@@ -137,6 +137,49 @@ def test_turbo_decode_golden_and_batch():
     assert abs(int((got != msgs).sum()) - int((want != msgs).sum())) <= max(10, 0.05 * (want != msgs).sum())
 
 
+def test_turbo_step_major_loop_shapes_priors_and_trellises():
+    """The turbo loop on step-major arrays (the default where the block-rescaled kernel applies) against the frame-major loop
+    with its interleaver kernels (CPB_OPT_TURBO_FRAME_MAJOR: same MAP arithmetic, so the SAME bits) and against the fp64
+    oracle: ragged batches (frames padded to 32), frame lengths with 4-step tails, a single group, an a-priori L_int, 4- and
+    8-state RSC codes, short MAP windows."""
+    from commpy_b200 import _lib
+    from commpy_b200.channelcoding import Trellis, set_map_window
+    rs = np.random.RandomState(31)
+    k4 = helpers.rsc_k4()
+    k3 = Trellis(np.array([2]), np.array([[1, 5]]), np.array([[7]]), "rsc")
+    cases = [(k4, 5, 100, 3, False, 0), (k4, 33, 516, 4, True, 0), (k4, 70, 2048, 6, False, 0), (k4, 3, 4, 2, True, 0),
+             (k3, 37, 1000, 5, True, 0), (k4, 40, 6144, 6, False, 128), (k4, 9, 3072, 4, True, 256)]
+    for tr, batch, N, iters, prior, window in cases:
+        il = RandInterlv(N, 3)
+        s2 = 1.0 / (2 * (1 / 3) * 10 ** (1.5 / 10))
+        ys, y1, y2, msgs = [], [], [], []
+        for b in range(batch):
+            msg = rs.randint(0, 2, N)
+            s_, p1, p2 = turbo_encode(msg, tr, tr, il)
+            ys.append(2.0 * s_[:N] - 1 + np.sqrt(s2) * rs.randn(N))
+            y1.append(2.0 * p1[:N] - 1 + np.sqrt(s2) * rs.randn(N))
+            y2.append(2.0 * p2[:N] - 1 + np.sqrt(s2) * rs.randn(N))
+            msgs.append(msg)
+        ys, y1, y2, msgs = map(np.stack, (ys, y1, y2, msgs))
+        La = (1.5 * (2.0 * msgs - 1) + rs.randn(batch, N)) if prior else None      # a helpful, noisy prior
+        got = {}
+        set_map_window(window)
+        try:
+            for fm in (1, 0):
+                _lib.set_option(_lib.OPT_TURBO_FRAME_MAJOR, fm)
+                got[fm] = turbo_decode_batch(ys, y1, y2, tr, s2, iters, il, La).cpu().numpy()
+        finally:
+            _lib.set_option(_lib.OPT_TURBO_FRAME_MAJOR, 0)
+            set_map_window(0)
+        assert np.array_equal(got[0], got[1]), (batch, N, int((got[0] != got[1]).sum()))
+        want = np.stack([oracle.turbo_decode(ys[b], y1[b], y2[b], tr, s2, iters, il, None if La is None else La[b])
+                         for b in range(min(batch, 6))])
+        agree = (got[0][:len(want)] == want).mean()
+        assert agree >= 0.999 or N < 64, (batch, N, float(agree))
+        if N < 64:
+            assert (got[0][:len(want)] != want).sum() <= 1
+
+
 # ---------------------------------------------------------------- LDPC
 def _golden_ldpc(c):
     import scipy.sparse as sp
