@@ -420,7 +420,8 @@ class TurboWorkload(Workload):
     def e2e_step(self):
         from commpy_b200.channelcoding import set_map_window, suggest_map_window, turbo_decode_batch_host
         set_map_window(suggest_map_window(min(self.batch, 2048), self.N))     # the host pipeline decodes chunks of <= 2,048 codewords
-        self.e2e_bits = turbo_decode_batch_host(self.h_np[0], self.h_np[1], self.h_np[2], self.trellis, self.s2, self.iters, self.il)
+        self.e2e_bits = turbo_decode_batch_host(self.h_np[0], self.h_np[1], self.h_np[2], self.trellis, self.s2, self.iters, self.il,
+                                                out=self.h_out)
 
     def e2e_alt(self):
         return None
@@ -505,12 +506,13 @@ class LdpcWorkload(Workload):
     def e2e_setup(self, torch):
         self.h_llr = self.llr.cpu().pin_memory()
         self.h_np = self.h_llr.numpy()
+        self.h_dec = torch.empty((self.batch, self.n), dtype=torch.uint8).pin_memory()
         return {"frames_per_call": self.batch, "h2d": self.batch * self.n * 4, "d2h": self.batch * self.n,
                 "api": "commpy_b200.channelcoding.ldpc_bp_decode_batch_host(pinned host array) -> cpb_ldpc_decode_host"}
 
     def e2e_step(self):
         from commpy_b200.channelcoding import ldpc_bp_decode_batch_host
-        self.e2e_dec = ldpc_bp_decode_batch_host(self.h_np, self.params, self.iters, "fp32", return_llrs=False)
+        self.e2e_dec = ldpc_bp_decode_batch_host(self.h_np, self.params, self.iters, "fp32", return_llrs=False, out=self.h_dec)
 
     def e2e_alt(self):
         return None

@@ -14,7 +14,7 @@ CPB_OK, CPB_EINVAL, CPB_EUNSUPPORTED, CPB_ECUDA, CPB_ENOMEM, CPB_ETRELLIS = rang
 CPB_U8, CPB_F32 = 0, 1
 VITERBI_MODES = {"hard": 0, "soft": 1, "unquantized": 2}
 LDPC_FP32, LDPC_FP64 = 0, 1
-OPT_VITERBI_FORCE_GENERIC, OPT_LDPC_NO_BULK, OPT_BCJR_WINDOW, OPT_BCJR_PER_STEP_SCALING, OPT_TURBO_FRAME_MAJOR = 0, 1, 2, 3, 4
+OPT_VITERBI_FORCE_GENERIC, OPT_LDPC_NO_BULK, OPT_BCJR_WINDOW, OPT_BCJR_PER_STEP_SCALING, OPT_TURBO_FRAME_MAJOR, OPT_TX_FORCE_GENERIC = 0, 1, 2, 3, 4, 5
 
 # every symbol include/commpy_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [

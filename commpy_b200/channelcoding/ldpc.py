@@ -142,10 +142,10 @@ def ldpc_bp_decode_batch(llr, ldpc_code_params, n_iters, precision="fp32", retur
 
 
 def ldpc_bp_decode_batch_host(llr, ldpc_code_params, n_iters, precision="fp32", return_llrs=True, return_iters=False,
-                              decoder_algorithm="MSA"):
+                              decoder_algorithm="MSA", out=None):
     """The same for a HOST array through the pipelined host entry point (cpb_ldpc_decode_host): `llr` is a C-contiguous
     numpy (batch, n) array of the precision's dtype and is clipped IN PLACE to +-500 like the reference (ldpc.py:186).
-    Returns numpy arrays: dec (batch, n) uint8 [, out_llrs] [, iterations int32]."""
+    Returns numpy arrays: dec (batch, n) uint8 [, out_llrs] [, iterations int32]; `out` (e.g. a pinned buffer) receives dec."""
     _lib.require_cuda()
     if decoder_algorithm not in ("MSA", "SPA"):
         raise NameError('Please input a valid decoder_algorithm string (meanning "SPA" or "MSA").')
@@ -155,7 +155,8 @@ def ldpc_bp_decode_batch_host(llr, ldpc_code_params, n_iters, precision="fp32", 
     if x.ndim != 2 or x.shape[1] != n:
         raise ValueError("llr must be (batch, n_vnodes)")
     batch = x.shape[0]
-    dec = np.empty((batch, n), dtype=np.uint8)
+    from .turbo import _host_out
+    dec = _host_out(out, (batch, n), np.uint8, "out")
     out = np.empty((batch, n), dtype=dt) if return_llrs else None
     iters = np.empty((batch,), dtype=np.int32) if return_iters else None
     rc = _lib.load().cpb_ldpc_decode_host(handle, 0 if decoder_algorithm == "MSA" else 1, _lib.ptr(x),

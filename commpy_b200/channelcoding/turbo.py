@@ -82,10 +82,21 @@ def map_decode_batch_host(sys_symbols, non_sys_symbols, trellis, noise_variance,
     return L, bits
 
 
+def _host_out(out, shape, dtype, what):
+    """caller-supplied host output (numpy array or CPU torch tensor; pinned memory keeps the D2H copies asynchronous, a
+    pageable destination makes every chunk's copy-back block the host and serialises the pipeline) or a fresh array"""
+    if out is None:
+        return np.empty(shape, dtype=dtype)
+    arr = out.numpy() if hasattr(out, "numpy") and not isinstance(out, np.ndarray) else out
+    if not isinstance(arr, np.ndarray) or arr.shape != tuple(shape) or arr.dtype != np.dtype(dtype) or not arr.flags["C_CONTIGUOUS"]:
+        raise ValueError("%s must be a C-contiguous %s host array of shape %s" % (what, np.dtype(dtype).name, tuple(shape)))
+    return arr
+
+
 def turbo_decode_batch_host(sys_symbols, non_sys_symbols_1, non_sys_symbols_2, trellis, noise_variance,
-                            number_iterations, interleaver, L_int=None):
+                            number_iterations, interleaver, L_int=None, out=None):
     """Batched turbo decoder for HOST arrays through the pipelined host entry point (cpb_turbo_decode_host):
-    (batch, N) float arrays -> (batch, N) uint8 numpy array."""
+    (batch, N) float arrays -> (batch, N) uint8 numpy array (`out`, if given: e.g. a pinned buffer)."""
     _lib.require_cuda()
     s = np.ascontiguousarray(sys_symbols, dtype=np.float32)
     p1 = np.ascontiguousarray(non_sys_symbols_1, dtype=np.float32)
@@ -95,7 +106,7 @@ def turbo_decode_batch_host(sys_symbols, non_sys_symbols_1, non_sys_symbols_2, t
     batch, N = s.shape
     perm = _checked_perm(interleaver, N)
     la = None if L_int is None else np.ascontiguousarray(L_int, dtype=np.float32)
-    bits = np.empty((batch, N), dtype=np.uint8)
+    bits = _host_out(out, (batch, N), np.uint8, "out")
     rc = _lib.load().cpb_turbo_decode_host(_trellis_handle(trellis), _lib.ptr(s), _lib.ptr(p1), _lib.ptr(p2), _lib.ptr(perm),
                                            C.c_int64(batch), C.c_int64(N), C.c_float(noise_variance), int(number_iterations),
                                            _lib.ptr(la), _lib.ptr(bits))

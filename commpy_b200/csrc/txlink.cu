@@ -153,6 +153,80 @@ __global__ void __launch_bounds__(128) conv_link_tx_kernel(const Params p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Word-parallel form of the kernel above for the common link: n = 2 outputs per input bit, no puncturing, 2 / 4 / 8 bits per
+// symbol (QPSK, 16-QAM, 256-QAM) and frames of whole 128-bit message blocks.  Same random streams, same outputs (the test
+// suite compares the two kernels bit for bit), ~5x fewer instructions per symbol:
+//   * a thread owns ONE Philox message block (128 information bits = 256 / nb symbols) and encodes 32 bits at a time: the
+//     coded stream of output j is the XOR of the message word delayed by each set tap (funnel shifts across the word
+//     boundary) -- ~25 instructions per 32 bits instead of a popcount per bit and output;
+//   * a symbol's nb coded bits are nb/2 consecutive bits of each of the two coded words: the constellation is re-indexed once
+//     per CTA by (bits of output 0 | bits of output 1 << nb/2), so mapping is two bit-field extracts and one 8-byte load;
+//   * message bytes leave as 16-byte stores (4 bits -> 4 bytes by one multiply), symbols as 16-byte stores (the two symbols
+//     that share a Philox noise block).
+// ------------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(128) conv_link_tx_fast_kernel(const Params p)
+{
+    constexpr int H = NB / 2;                    // information bits per symbol
+    constexpr int SPW = 32 / H;                  // symbols per 32-bit message word
+    __shared__ float2 s_map[1 << NB];
+    for (int k = threadIdx.x; k < (1 << NB); k += blockDim.x) {
+        // k = a | b << H, a / b = H consecutive bits of output 0 / 1 (bit i = step t+i); the modem's index takes the coded
+        // bits in transmission order c0[t], c1[t], c0[t+1], ... MSB first (modulation.py:93-96)
+        int idx = 0;
+#pragma unroll
+        for (int i = 0; i < H; ++i) idx |= (((k >> i) & 1) << (NB - 1 - 2 * i)) | (((k >> (H + i)) & 1) << (NB - 2 - 2 * i));
+        s_map[k] = p.cst[idx];
+    }
+    __syncthreads();
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= p.frames * p.chunks) return;
+    const int64_t fl = gid / p.chunks;                       // frame within this call
+    const uint32_t b = (uint32_t)(gid - fl * p.chunks);      // message block of the frame
+    const uint64_t fg = (uint64_t)(p.first_frame + fl);
+    const uint32_t f_lo = (uint32_t)fg, f_hi = (uint32_t)(fg >> 32);
+
+    const uint4 blk = philox4x32_10(make_uint4(f_lo, f_hi, b, 0u), p.seed_lo, p.seed_hi);
+    uint32_t prev = 0u;                                      // the 32 message bits before this block (state 0 before bit 0)
+    if (b > 0) prev = philox4x32_10(make_uint4(f_lo, f_hi, b - 1u, 0u), p.seed_lo, p.seed_hi).w;
+    const uint32_t word[4] = {blk.x, blk.y, blk.z, blk.w};
+
+    uint8_t *msg = p.msg + fl * p.frame_bits + (int64_t)b * 128;
+    float2 *y = p.y + fl * p.nsym + (int64_t)b * (4 * SPW);
+    const uint32_t g0 = p.g[0], g1 = p.g[1];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t cur = word[w];
+        // message bytes: bit i of a nibble -> byte i (x * 0x00204081 puts bit i at 8 i, stray products land on other bits)
+        uint32_t mb[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) mb[q] = (((cur >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;
+        *reinterpret_cast<uint4 *>(msg + 32 * w) = make_uint4(mb[0], mb[1], mb[2], mb[3]);
+        *reinterpret_cast<uint4 *>(msg + 32 * w + 16) = make_uint4(mb[4], mb[5], mb[6], mb[7]);
+        // coded words: c_j bit i = XOR over taps d of u_{t+i-d}
+        uint32_t c0 = 0u, c1 = 0u;
+        for (int d = 0; d <= p.mem; ++d) {
+            const uint32_t dl = d ? __funnelshift_l(prev, cur, d) : cur;
+            if ((g0 >> d) & 1u) c0 ^= dl;
+            if ((g1 >> d) & 1u) c1 ^= dl;
+        }
+        prev = cur;
+#pragma unroll
+        for (int s2 = 0; s2 < SPW; s2 += 2) {
+            const uint32_t sym = (uint32_t)(w * SPW + s2);               // even: symbols sym, sym+1 share a noise block
+            const uint32_t gs = b * (4u * SPW) + sym;                    // symbol index within the frame
+            const uint4 r = philox4x32_10(make_uint4(f_lo, f_hi, gs >> 1, 1u), p.seed_lo, p.seed_hi);
+            const float2 n0 = box_muller(r.x, r.y), n1 = box_muller(r.z, r.w);
+            const uint32_t k0 = ((c0 >> (H * s2)) & ((1u << H) - 1u)) | (((c1 >> (H * s2)) & ((1u << H) - 1u)) << H);
+            const uint32_t k1 = ((c0 >> (H * (s2 + 1))) & ((1u << H) - 1u)) | (((c1 >> (H * (s2 + 1))) & ((1u << H) - 1u)) << H);
+            const float2 a0 = s_map[k0], a1 = s_map[k1];
+            *reinterpret_cast<float4 *>(y + sym) = make_float4(fmaf(p.sigma, n0.x, a0.x), fmaf(p.sigma, n0.y, a0.y),
+                                                               fmaf(p.sigma, n1.x, a1.x), fmaf(p.sigma, n1.y, a1.y));
+        }
+    }
+}
+
 static int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
 
 }  // namespace txlink
@@ -221,6 +295,20 @@ static int conv_link_tx_impl(const cpbTrellis *t, const cpbModem *m, int64_t fra
     p.cst = reinterpret_cast<const float2 *>(cst);
     p.msg = msg_dev;
     p.y = reinterpret_cast<float2 *>(y_dev);
+    // word-parallel kernel: n = 2, no puncturing, 2 / 4 / 8 bits per symbol, whole 128-bit message blocks, 16-byte aligned rows
+    const bool fast = !punct_vec && n == 2 && (nb == 2 || nb == 4 || nb == 8) && Mc == (1 << nb) && (frame_bits % 128) == 0 &&
+                      mem >= 1 && mem < 32 && (reinterpret_cast<uintptr_t>(msg_dev) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(y_dev) & 15) == 0 && !option(CPB_OPT_TX_FORCE_GENERIC);
+    if (fast) {
+        p.chunks = frame_bits / 128;
+        const int64_t threads = frames * p.chunks;
+        const unsigned grid = (unsigned)ceil_div(threads, 128);
+        if (nb == 2) txlink::conv_link_tx_fast_kernel<2><<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+        else if (nb == 4) txlink::conv_link_tx_fast_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+        else txlink::conv_link_tx_fast_kernel<8><<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+        CPB_LAUNCH_CHECK();
+        return CPB_OK;
+    }
     const int64_t threads = frames * p.chunks;
     const unsigned grid = (unsigned)ceil_div(threads, 128);
     txlink::conv_link_tx_kernel<<<grid, 128, (size_t)Mc * sizeof(float2), (cudaStream_t)stream>>>(p);

@@ -51,6 +51,7 @@ int cpb_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *global_
                                              which rescales every 4th step and falls back per block on decay)          */
 #define CPB_OPT_TURBO_FRAME_MAJOR 4       /* 1: turbo loop on frame-major arrays with separate interleaver kernels (the cross-check
                                              of the default, which transposes once and indexes rows through the interleaver) */
+#define CPB_OPT_TX_FORCE_GENERIC 5        /* 1: cpb_conv_link_tx always runs the bit-serial kernel (cross-check of the word-parallel one) */
 #define CPB_OPT_COUNT 8
 int cpb_set_option(int option_id, int value);
 int cpb_get_option(int option_id, int *value);

@@ -189,6 +189,28 @@ def test_conv_link_tx_kernel_matches_numpy_model(modem_m, frame_bits):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("modem_m", [4, 16, 256])
+def test_conv_link_tx_word_parallel_kernel_equals_bit_serial(modem_m):
+    """The word-parallel TX kernel (n = 2, no puncturing, 2 / 4 / 8 bits per symbol, 128-bit message blocks) and the bit-serial
+    one (CPB_OPT_TX_FORCE_GENERIC) produce the same message bytes and the same received symbols, noise included."""
+    import torch
+    from commpy_b200 import _lib
+    from commpy_b200.links import conv_link_tx
+    from commpy_b200.modulation import QAMModem
+    modem = QAMModem(modem_m)
+    for tr, frame_bits in ((helpers.k7(), 1024), (helpers.k7_wifi_quirk(), 128), (helpers.k7(), 4096)):
+        out = {}
+        for force in (1, 0):
+            _lib.set_option(_lib.OPT_TX_FORCE_GENERIC, force)
+            try:
+                out[force] = conv_link_tx(tr, modem, 37, frame_bits, 0xfeedbeef12345, (1 << 32) - 5, 0.6)
+            finally:
+                _lib.set_option(_lib.OPT_TX_FORCE_GENERIC, 0)
+        assert torch.equal(out[0][0], out[1][0])
+        assert torch.equal(torch.view_as_real(out[0][1]), torch.view_as_real(out[1][1]))
+
+
+@pytest.mark.gpu
 def test_dropin_linkmodel_with_gpu_receiver_and_decoder():
     """commpy/examples/conv_encode_decode.py:99-127 shape: QPSK, (5,7) code, hard and unquantized Viterbi via LinkModel."""
     from commpy_b200.channelcoding import Trellis, conv_encode, viterbi_decode
