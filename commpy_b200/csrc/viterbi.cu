@@ -99,9 +99,15 @@ constexpr int BD = 32;             // one warp per CTA: every synchronisation be
 constexpr int QBITS = 17;          // soft / unquantized: |quantised value| <= 2^17 (22 metric bits: 27 * 2^17 < 2^22)
 constexpr int QMAX = 1 << QBITS;
 constexpr int DMAX = 46;           // deepest traceback the fast path takes
-constexpr int TASK_CAP = 384;
+#ifndef CPB_TASK_CAP
+#define CPB_TASK_CAP 384
+#endif
+constexpr int TASK_CAP = CPB_TASK_CAP;
 #ifndef CPB_VITERBI_TBB
 #define CPB_VITERBI_TBB 24         // windows per traceback block (multiple of B, <= 28)
+#endif
+#ifndef CPB_VITERBI_TBB_SOFT
+#define CPB_VITERBI_TBB_SOFT CPB_VITERBI_TBB    // the same for the one-frame-per-thread (float input) kernels
 #endif      // retired paths kept per block and warp; beyond that they are finished inline
 
 struct Params {
@@ -798,7 +804,10 @@ static int launch(const Params &p, cudaStream_t st)
     void (*kern)(const Params) = (IOP == 1) ? viterbi_fast_kernel_hard_packed<CODE>
                                : (IOP == 2) ? viterbi_fast_kernel_soft_punct<CODE>
                                : (PACK == 2) ? viterbi_fast_kernel_hard<CODE> : viterbi_fast_kernel_soft<CODE>;
-    { const int rc_ = ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem); if (rc_) return rc_; }
+#ifndef CPB_SOFT_MAX_CARVEOUT
+#define CPB_SOFT_MAX_CARVEOUT 0
+#endif
+    { const int rc_ = ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem, PACK == 1 && CPB_SOFT_MAX_CARVEOUT); if (rc_) return rc_; }
     const int64_t grid = ceil_div(p.batch, (int64_t)BD * PACK);
     kern<<<(unsigned)grid, BD, smem, st>>>(p);
     CPB_LAUNCH_CHECK();
@@ -1117,7 +1126,7 @@ int cpb_viterbi_decode(const cpbTrellis *t, const void *coded_dev, int in_dtype,
         fast::Params p{};
         p.coded = coded_dev; p.n_in = n_in; p.batch = batch;
         p.L = (int)L; p.T = (int)T; p.D = D;
-        p.TBB = CPB_VITERBI_TBB;
+        p.TBB = (mode == CPB_VITERBI_HARD) ? CPB_VITERBI_TBB : CPB_VITERBI_TBB_SOFT;
         p.NJ = (D > 8) ? (D - 8 + fast::B - 1) / fast::B : 0;
         p.RB = p.NJ + p.TBB / fast::B;
         p.mode = mode; p.out = out_bits_dev;
@@ -1235,7 +1244,7 @@ int cpb_viterbi_decode_punctured(const cpbTrellis *t, const float *llr_punct_dev
     fast::Params p{};
     p.coded = llr_punct_dev; p.n_in = n_depunct; p.batch = batch;
     p.L = (int)L; p.T = (int)T; p.D = D;
-    p.TBB = CPB_VITERBI_TBB;
+    p.TBB = CPB_VITERBI_TBB_SOFT;
     p.NJ = (D > 8) ? (D - 8 + fast::B - 1) / fast::B : 0;
     p.RB = p.NJ + p.TBB / fast::B;
     p.mode = mode; p.out = out_bits_dev;
