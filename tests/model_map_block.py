@@ -13,8 +13,8 @@ FLOOR = F(2.0 ** -20)
 
 def _weights(ys, yp, la, c2):
     l = np.clip(la * LOG2E, F(-60), F(60)).astype(F)
-    lu = (np.clip(ys * c2, F(-120), F(120)) + l).astype(F)
-    lb = np.clip(yp * c2, F(-120), F(120)).astype(F)
+    lu = (ys * c2 + l).astype(F)                        # (no clamp on the channel terms: 2^-|x| of a huge |x| is 0)
+    lb = (yp * c2).astype(F)
     eu, eb = np.exp2(-np.abs(lu)).astype(F), np.exp2(-np.abs(lb)).astype(F)
     one = np.ones_like(eu)
     u1, u0 = np.where(lu >= 0, one, eu), np.where(lu >= 0, eu, one)

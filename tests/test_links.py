@@ -198,7 +198,9 @@ def test_conv_link_tx_word_parallel_kernel_equals_bit_serial(modem_m):
     from commpy_b200.links import conv_link_tx
     from commpy_b200.modulation import QAMModem
     modem = QAMModem(modem_m)
-    for tr, frame_bits in ((helpers.k7(), 1024), (helpers.k7_wifi_quirk(), 128), (helpers.k7(), 4096)):
+    from commpy_b200.channelcoding import Trellis
+    k3 = Trellis(np.array([2]), np.array([[5, 7]]))
+    for tr, frame_bits in ((helpers.k7(), 1024), (helpers.k7_wifi_quirk(), 128), (helpers.k7(), 4096), (k3, 256)):
         out = {}
         for force in (1, 0):
             _lib.set_option(_lib.OPT_TX_FORCE_GENERIC, force)
