@@ -32,6 +32,8 @@ N = 2048
 ys, y1, y2 = (torch.randn(6, N, device="cuda") * 0.8 - 1 for _ in range(3))
 map_decode_batch(ys, y1, rsc, 0.64, torch.zeros(6, N, device="cuda"))
 turbo_decode_batch(ys, y1, y2, rsc, 0.64, 2, RandInterlv(N, 1))
+turbo_decode_batch(ys[:, :516].contiguous(), y1[:, :516].contiguous(), y2[:, :516].contiguous(), rsc, 0.64, 2, RandInterlv(516, 2),
+                   torch.randn(6, 516, device="cuda"))            # step-major loop, 4-step tail segment, a-priori L_int
 ys, y1 = (torch.randn(5, 301, device="cuda") - 1 for _ in range(2))
 map_decode_batch(ys, y1, rsc, 0.7, torch.zeros(5, 301, device="cuda"))
 # LDPC: bulk-copy check pass (>= 128 frames), small batch, fp64, SPA
