@@ -18,7 +18,7 @@ OPT_VITERBI_FORCE_GENERIC, OPT_LDPC_NO_BULK, OPT_BCJR_WINDOW, OPT_BCJR_PER_STEP_
 
 # every symbol include/commpy_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "cpb_strerror", "cpb_last_cuda_error", "cpb_version", "cpb_device_info", "cpb_set_option", "cpb_get_option",
+    "cpb_strerror", "cpb_last_cuda_error", "cpb_version", "cpb_device_info", "cpb_release_scratch", "cpb_set_option", "cpb_get_option",
     "cpb_trellis_create", "cpb_trellis_destroy", "cpb_trellis_fast_path",
     "cpb_viterbi_sizes", "cpb_viterbi_workspace_bytes", "cpb_viterbi_decode", "cpb_viterbi_decode_host", "cpb_viterbi_decode_packed", "cpb_viterbi_decode_host_packed",
     "cpb_viterbi_punctured_workspace_bytes", "cpb_viterbi_decode_punctured",
@@ -72,6 +72,11 @@ def check(status, what=""):
 def set_option(option_id, value):
     """cpb_set_option: explicit test / cross-check switches (the library never reads the environment)."""
     check(load().cpb_set_option(int(option_id), int(value)), "set_option")
+
+
+def release_scratch():
+    """cpb_release_scratch: hand the unused part of the library's device scratch pool back to the driver."""
+    check(load().cpb_release_scratch(), "release_scratch")
 
 
 def require_cuda():

@@ -73,6 +73,19 @@ int ensure_dyn_smem(const void *kernel, size_t bytes, bool max_carveout)
     return CPB_OK;
 }
 
+static std::mutex g_pool_mu;
+static std::unordered_map<int, cudaMemPool_t> g_pools;      // device -> the library's scratch pool
+
+int release_scratch_pool()
+{
+    int dev = 0;
+    CPB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    auto it = g_pools.find(dev);
+    if (it != g_pools.end()) CPB_CUDA(cudaMemPoolTrimTo(it->second, 0));
+    return CPB_OK;
+}
+
 int Scratch::acquire(void *user, size_t user_bytes, size_t need, cudaStream_t s)
 {
     stream = s;
@@ -85,13 +98,12 @@ int Scratch::acquire(void *user, size_t user_bytes, size_t need, cudaStream_t s)
     // the library's own stream-ordered pool (one per device), which keeps what it has been given: with the default pool's
     // release threshold of 0 every synchronisation returned the scratch to the driver and the next call paid for gigabytes
     // of fresh physical memory (the host-buffer pipelines synchronise once per call)
-    static std::mutex mu;
-    static std::unordered_map<int, cudaMemPool_t> pools;
     int dev = 0;
     CPB_CUDA(cudaGetDevice(&dev));
     cudaMemPool_t pool = nullptr;
     {
-        std::lock_guard<std::mutex> lock(mu);
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        auto &pools = g_pools;
         auto it = pools.find(dev);
         if (it == pools.end()) {
             cudaMemPoolProps props{};
@@ -146,6 +158,8 @@ int cpb_get_option(int option_id, int *value)
     *value = cpb::option(option_id);
     return CPB_OK;
 }
+
+int cpb_release_scratch(void) { return cpb::release_scratch_pool(); }
 
 int cpb_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *global_mem_bytes)
 {

@@ -38,6 +38,10 @@ struct Scratch {
     void release();
 };
 
+// the decoders' scratch comes from a library-owned stream-ordered pool (one per device) that keeps what it has been given;
+// this hands the unused part back to the driver (cpb_release_scratch)
+int release_scratch_pool();
+
 // cudaFuncAttributeMaxDynamicSharedMemorySize opt-in, made once per (kernel, device) and size: launches do not pay for it
 int ensure_dyn_smem(const void *kernel, size_t bytes, bool max_carveout = false);
 

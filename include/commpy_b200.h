@@ -41,6 +41,10 @@ const char *cpb_strerror(int status);
 const char *cpb_last_cuda_error(void);
 int cpb_version(void);                     /* 10000*major + 100*minor + patch */
 int cpb_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *global_mem_bytes);
+/* Decoder calls made without a caller workspace take their scratch from a library-owned stream-ordered memory pool of the
+ * current device, which keeps the memory for the next call (a call must not pay for gigabytes of fresh device memory).
+ * cpb_release_scratch() returns whatever is not in use to the driver; no reference counterpart (housekeeping). */
+int cpb_release_scratch(void);
 /* Explicit switches for tests and kernel cross-checks (process wide, default 0).  The library never reads the
  * environment.  They select between kernels that implement the SAME reference semantics. */
 #define CPB_OPT_VITERBI_FORCE_GENERIC 0   /* 1: every trellis goes through the table-driven Viterbi kernel */

@@ -180,6 +180,20 @@ def test_turbo_step_major_loop_shapes_priors_and_trellises():
             assert (got[0][:len(want)] != want).sum() <= 1
 
 
+def test_release_scratch_between_calls():
+    """cpb_release_scratch hands the library's scratch pool back to the driver; the next call allocates again and decodes the same."""
+    from commpy_b200 import _lib
+    tr = helpers.rsc_k4()
+    rs = np.random.RandomState(5)
+    ys, y1, y2 = (rs.randn(40, 1024) - 1 for _ in range(3))
+    il = RandInterlv(1024, 7)
+    a = turbo_decode_batch(ys, y1, y2, tr, 0.7, 3, il).cpu().numpy()
+    torch.cuda.synchronize()
+    _lib.release_scratch()
+    b = turbo_decode_batch(ys, y1, y2, tr, 0.7, 3, il).cpu().numpy()
+    assert np.array_equal(a, b)
+
+
 # ---------------------------------------------------------------- LDPC
 def _golden_ldpc(c):
     import scipy.sparse as sp
